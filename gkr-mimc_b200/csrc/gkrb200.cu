@@ -1,0 +1,926 @@
+// gkrb200: host driver + C ABI of the B200-native GKR-MiMC prover.  See include/gkrb200.h for the contract.
+//
+// Structure mirrors the reference call stack:
+//   gkrb200_gkr_prove_mimc   ~ gkr.Prove / updateWithSumcheck        (gkr/prover.go:21-91)
+//   Ctx::sumcheck            ~ sumcheck.Prove                        (sumcheck/prover.go:46-90)
+//   Ctx::build_eq            ~ makeEqTable                           (sumcheck/prover.go:102-144)
+//   round loop               ~ dispatchPartialEvals / InterpolateOnRange / GetChallenge / dispatchFolding
+// The device does all O(N) work; the host keeps only the O(bn) serial transcript.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <atomic>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../include/gkrb200.h"
+#include "kernels.cuh"
+#include "transcript.hpp"
+
+using gkr::FrRaw;
+namespace H = gkr::host;
+
+static_assert(sizeof(FrRaw) == 32 && sizeof(H::Fr) == 32, "element image must be 32 bytes");
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(x)                                                                                             \
+    do {                                                                                                        \
+        cudaError_t e_ = (x);                                                                                   \
+        if (e_ != cudaSuccess) return fail(GKRB200_ERR_CUDA, "%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define TRY(x)             \
+    do {                   \
+        int rc_ = (x);     \
+        if (rc_) return rc_; \
+    } while (0)
+
+extern "C" const char* gkrb200_last_error(void) { return g_err; }
+extern "C" const char* gkrb200_version(void) { return "gkrb200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------ NCCL (dlopen'ed)
+struct Nccl {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (h) return true;
+        // torch's bundled libnccl.so.2 is reused when it is already mapped in the process (same SONAME)
+        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return false;
+        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+    }
+};
+static Nccl g_nccl;
+#define NCCL_TRY(x)                                                                                               \
+    do {                                                                                                          \
+        ncclResult_t r_ = (x);                                                                                    \
+        if (r_ != ncclSuccess) return fail(GKRB200_ERR_COMM, "%s failed: %s", #x, g_nccl.GetErrorString(r_));     \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------ context
+enum KClass { KC_ASSIGN = 0, KC_EQ = 1, KC_ROUND = 2, KC_FOLD = 3, KC_MULTIEQ = 4, KC_STAGING = 5, KC_MISC = 6, KC_N = 8 };
+
+static constexpr int N_LAYERS = GKRB200_MIMC_LAYERS;
+static constexpr int MAX_CLAIMS = 91;
+static constexpr int ROUND_BLOCK = 128;
+static constexpr int MAX_EV = 9;
+
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct gkrb200_ctx {
+    int device = 0;
+    int n_sm = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int max_bn = 0;
+    size_t cap = 0;  // entries per table slot
+
+    // device arena
+    FrRaw* arena = nullptr;
+    FrRaw* layers = nullptr;     // [92][cap]: slot 0 = a[0] key (== a[2]), slot 1 = a[1] msg, slot s>=2 = a[s+1]
+    FrRaw* eq = nullptr;         // [cap]
+    FrRaw* scratch[3] = {};      // [cap/2] each, contiguous
+    FrRaw* hi = nullptr;         // [MAX_CLAIMS][2^ceil(max_bn/2)]
+    FrRaw* lo = nullptr;
+    FrRaw* d_q = nullptr;        // [MAX_CLAIMS*max_bn]
+    FrRaw* d_mults = nullptr;    // [MAX_CLAIMS]
+    FrRaw* partials = nullptr;   // [max_grid][MAX_EV]
+    unsigned int* ticket = nullptr;
+    FrRaw* d_local = nullptr;    // [16] this rank's contribution (multi-GPU)
+    FrRaw* d_all = nullptr;      // [8*16]
+    int max_grid = 0;
+
+    // pinned, device-mapped result slot
+    FrRaw* h_result = nullptr;  // [16]
+    volatile uint32_t* h_flag = nullptr;
+    uint32_t seq = 0;
+    H::Fr* h_stage = nullptr;  // pinned staging for qprimes/mults uploads [MAX_CLAIMS*(max_bn+1)]
+
+    // assignment state
+    size_t n_local = 0;  // entries per table on this rank
+    int bn = -1;         // global log2 batch of the current assignment
+    bool sharded = false;
+
+    // multi-GPU
+    int rank = 0, world = 1, log_world = 0;
+    ncclComm_t comm = nullptr;
+
+    // instrumentation
+    gkrb200_stats st{};
+    bool profiling = false;
+    struct Ev {
+        cudaEvent_t a, b;
+        int cls;
+    };
+    std::vector<Ev> ev_pool;
+    size_t ev_used = 0;
+
+    H::Lagrange lagrange;
+
+    FrRaw* slot(int layer) const {  // device table of Assignment[layer]
+        int s = layer == 2 ? 0 : (layer < 2 ? layer : layer - 1);
+        return layers + (size_t)s * cap;
+    }
+    int eff_world() const { return sharded ? world : 1; }
+
+    int ev_flush();
+    void prof_begin(int cls);
+    void prof_end();
+    int wait_flag(uint32_t seq);
+    int upload(FrRaw* dst, const void* src, size_t n_elems);
+
+    int build_eq(const H::Fr* qprimes, size_t n_q, int bn_local, const H::Fr* mults, FrRaw* out);
+    int sumcheck(const FrRaw* x0, const FrRaw* x1, int bn_total, const H::Fr* qprimes, size_t n_q, const H::Fr* claims, size_t n_claims,
+                 int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out);
+    int exchange_and_fetch(int nacc, H::Fr* out);
+};
+
+// ------------------------------------------------------------------------------------------------ profiling helpers
+void gkrb200_ctx::prof_begin(int cls) {
+    st.launches_total++;
+    st.launches[cls]++;
+    if (!profiling) return;
+    if (ev_used == ev_pool.size()) {
+        if (ev_pool.size() >= 4096) {
+            ev_flush();
+        } else {
+            Ev e;
+            cudaEventCreate(&e.a);
+            cudaEventCreate(&e.b);
+            ev_pool.push_back(e);
+        }
+    }
+    ev_pool[ev_used].cls = cls;
+    cudaEventRecord(ev_pool[ev_used].a, stream);
+}
+void gkrb200_ctx::prof_end() {
+    if (!profiling) return;
+    cudaEventRecord(ev_pool[ev_used].b, stream);
+    ev_used++;
+}
+int gkrb200_ctx::ev_flush() {
+    if (ev_used) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        for (size_t i = 0; i < ev_used; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev_pool[i].a, ev_pool[i].b);
+            st.kernel_ms[ev_pool[i].cls] += ms;
+        }
+        ev_used = 0;
+    }
+    return 0;
+}
+#define LAUNCH(ctx, cls, kernel, grid, block, smem, ...)                           \
+    do {                                                                           \
+        (ctx)->prof_begin(cls);                                                    \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);           \
+        (ctx)->prof_end();                                                         \
+    } while (0)
+
+// spin on the mapped flag; bail out if the stream died or after a generous timeout (never hang the box)
+int gkrb200_ctx::wait_flag(uint32_t want) {
+    const double t0 = now_ms();
+    unsigned spins = 0;
+    while (*h_flag != want) {
+        _mm_pause();
+        if ((++spins & 0xfff) == 0) {
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(GKRB200_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && *h_flag != want) {
+                // stream drained: give the write a moment to land, then give up
+                for (int i = 0; i < 100000 && *h_flag != want; i++) _mm_pause();
+                if (*h_flag != want) return fail(GKRB200_ERR_CUDA, "device finished without publishing result %u (have %u)", want, *h_flag);
+            }
+            if (now_ms() - t0 > 60000.0) return fail(GKRB200_ERR_CUDA, "timeout waiting for device result");
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    st.wait_ms += now_ms() - t0;
+    return 0;
+}
+
+int gkrb200_ctx::upload(FrRaw* dst, const void* src, size_t n_elems) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n_elems * sizeof(FrRaw), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+static inline int grid_for(size_t work_items, int block, int max_grid) {
+    size_t g = (work_items + (size_t)block - 1) / (size_t)block;
+    if (g < 1) g = 1;
+    if (g > (size_t)max_grid) g = (size_t)max_grid;
+    return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------ init / free
+extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* stream) {
+    if (!out || max_bn < 0 || max_bn > 26) return fail(GKRB200_ERR_ARG, "bad arguments to gkrb200_init (max_bn=%d)", max_bn);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(GKRB200_ERR_CUDA, "no CUDA device available (%s); gkrb200 has no CPU fallback", e == cudaSuccess ? "0 devices" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(GKRB200_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CUDA_TRY(cudaSetDevice(device));
+    gkrb200_ctx* c = new gkrb200_ctx();
+    c->device = device;
+    c->max_bn = max_bn;
+    c->cap = (size_t)1 << max_bn;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete c;
+        return fail(GKRB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    }
+    c->n_sm = prop.multiProcessorCount;
+    c->max_grid = c->n_sm * 8;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    const size_t half = c->cap / 2 > 0 ? c->cap / 2 : 1;
+    const int nsmall = (max_bn + 1) / 2;
+    const size_t small = (size_t)1 << nsmall;
+    size_t total = 92 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
+                   (size_t)c->max_grid * MAX_EV + 16 + 8 * 16 + 64;
+    cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
+    if (me != cudaSuccess) {
+        delete c;
+        return fail(GKRB200_ERR_OOM, "cudaMalloc of %.2f GiB arena failed: %s", total * 32.0 / (1 << 30), cudaGetErrorString(me));
+    }
+    FrRaw* p = c->arena;
+    c->layers = p; p += 92 * c->cap;
+    c->eq = p; p += c->cap;
+    for (int i = 0; i < 3; i++) { c->scratch[i] = p; p += half; }
+    c->hi = p; p += MAX_CLAIMS * small;
+    c->lo = p; p += MAX_CLAIMS * small;
+    c->d_q = p; p += (size_t)MAX_CLAIMS * (max_bn + 1);
+    c->d_mults = p; p += MAX_CLAIMS;
+    c->partials = p; p += (size_t)c->max_grid * MAX_EV;
+    c->d_local = p; p += 16;
+    c->d_all = p; p += 8 * 16;
+    CUDA_TRY(cudaMalloc(&c->ticket, 64));
+    CUDA_TRY(cudaMemset(c->ticket, 0, 64));
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 16 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
+    c->h_flag = (volatile uint32_t*)(c->h_result + 16);
+    *c->h_flag = 0;
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_stage, (size_t)MAX_CLAIMS * (max_bn + 2) * sizeof(H::Fr), cudaHostAllocDefault));
+    // opt in to the dynamic shared memory the round kernels need
+    const int smem9 = 9 * 8 * ROUND_BLOCK * 4, smem3 = 3 * 8 * ROUND_BLOCK * 4;
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    *out = c;
+    return 0;
+}
+
+extern "C" void gkrb200_free(gkrb200_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (auto& e : c->ev_pool) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    cudaFree(c->arena);
+    cudaFree(c->ticket);
+    cudaFreeHost(c->h_result);
+    cudaFreeHost(c->h_stage);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int gkrb200_comm_unique_id(uint8_t id_out[128]) {
+    if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl: %s", dlerror());
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return 0;
+}
+extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint8_t uid[128]) {
+    if (!c || world < 1 || world > 8 || (world & (world - 1)) || rank < 0 || rank >= world)
+        return fail(GKRB200_ERR_ARG, "bad rank/world %d/%d (world must be a power of two <= 8)", rank, world);
+    c->rank = rank;
+    c->world = world;
+    c->log_world = 0;
+    while ((1 << c->log_world) < world) c->log_world++;
+    if (world == 1) return 0;
+    if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl: %s", dlerror());
+    CUDA_TRY(cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(id.internal, uid, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 assign
+static int assign_common(gkrb200_ctx* c, size_t n_local) {
+    const int block = 128;
+    const int grid = grid_for(n_local, block, c->n_sm * 16);
+    LAUNCH(c, KC_ASSIGN, gkr::k_mimc_assign, grid, block, 0, c->slot(0), c->slot(1), c->slot(3), c->cap, n_local);
+    c->st.fr_mul_assign += 364ull * n_local;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+static int check_n(gkrb200_ctx* c, size_t n, int* bn_out) {
+    if (!c) return fail(GKRB200_ERR_ARG, "null context");
+    if (n == 0 || (n & (n - 1))) return fail(GKRB200_ERR_ARG, "table size %zu is not a power of two", n);
+    int bn = 0;
+    while (((size_t)1 << bn) < n) bn++;
+    if (bn > c->max_bn) return fail(GKRB200_ERR_OOM, "batch 2^%d exceeds the context capacity 2^%d", bn, c->max_bn);
+    *bn_out = bn;
+    return 0;
+}
+
+extern "C" int gkrb200_mimc_assign(gkrb200_ctx* c, const uint64_t* key, const uint64_t* msg, size_t n, uint64_t* out93) {
+    int bn;
+    TRY(check_n(c, n, &bn));
+    if (!key || !msg) return fail(GKRB200_ERR_ARG, "null input table");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->sharded = c->world > 1 && bn > c->log_world;
+    c->bn = bn;
+    if (!c->sharded) {
+        c->n_local = n;
+        TRY(c->upload(c->slot(0), key, n));
+        TRY(c->upload(c->slot(1), msg, n));
+    } else {
+        // every rank receives the full tables and keeps entries {i : i mod world == rank}
+        c->n_local = n / (size_t)c->world;
+        FrRaw* tmp_key = c->eq;          // cap entries
+        FrRaw* tmp_msg = c->scratch[0];  // 3*cap/2 contiguous entries
+        TRY(c->upload(tmp_key, key, n));
+        TRY(c->upload(tmp_msg, msg, n));
+        const int grid = grid_for(c->n_local, 256, c->n_sm * 8);
+        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_key, c->slot(0), c->n_local, c->world, c->rank);
+        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_msg, c->slot(1), c->n_local, c->world, c->rank);
+    }
+    TRY(assign_common(c, c->n_local));
+    if (out93) CUDA_TRY(cudaMemcpyAsync(out93, c->slot(93), c->n_local * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gkrb200_mimc_assign_device(gkrb200_ctx* c, const void* d_key, const void* d_msg, size_t n) {
+    int bn;
+    TRY(check_n(c, n, &bn));
+    if (!d_key || !d_msg) return fail(GKRB200_ERR_ARG, "null input table");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->sharded = c->world > 1 && bn > c->log_world;
+    c->bn = bn;
+    if (!c->sharded) {
+        c->n_local = n;
+        CUDA_TRY(cudaMemcpyAsync(c->slot(0), d_key, n * sizeof(FrRaw), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->slot(1), d_msg, n * sizeof(FrRaw), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        c->n_local = n / (size_t)c->world;
+        const int grid = grid_for(c->n_local, 256, c->n_sm * 8);
+        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, (const FrRaw*)d_key, c->slot(0), c->n_local, c->world, c->rank);
+        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, (const FrRaw*)d_msg, c->slot(1), c->n_local, c->world, c->rank);
+    }
+    TRY(assign_common(c, c->n_local));
+    return 0;  // asynchronous on the context's stream
+}
+
+extern "C" int gkrb200_assign_layer_to_host(gkrb200_ctx* c, int layer, uint64_t* dst, size_t n) {
+    if (!c || !dst || layer < 0 || layer >= N_LAYERS) return fail(GKRB200_ERR_ARG, "bad layer %d", layer);
+    if (c->bn < 0) return fail(GKRB200_ERR_STATE, "no assignment in this context");
+    if (n != c->n_local) return fail(GKRB200_ERR_ARG, "layer has %zu entries on this rank, caller asked for %zu", c->n_local, n);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpyAsync(dst, c->slot(layer), n * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ K2/K5 eq table
+// out[x] = sum_j mults[j] * eq(q_j, x) over bn_local variables (mults == nullptr: single table with seed 1)
+int gkrb200_ctx::build_eq(const H::Fr* qprimes, size_t n_q, int bnl, const H::Fr* mults, FrRaw* out) {
+    if (n_q < 1 || n_q > (size_t)MAX_CLAIMS) return fail(GKRB200_ERR_ARG, "unsupported number of claims %zu (max %d)", n_q, MAX_CLAIMS);
+    const int nh = bnl / 2, nl = bnl - nh;  // nl <= ceil(max_bn/2)
+    const size_t n = (size_t)1 << bnl;
+    // stage q's (and multipliers) through pinned memory
+    size_t nq_el = n_q * (size_t)bnl;
+    if (nq_el) memcpy(h_stage, qprimes, nq_el * sizeof(H::Fr));
+    if (mults) memcpy(h_stage + nq_el, mults, n_q * sizeof(H::Fr));
+    if (nq_el) TRY(upload(d_q, h_stage, nq_el));
+    if (mults) TRY(upload(d_mults, h_stage + nq_el, n_q));
+    const int cls = n_q > 1 ? KC_MULTIEQ : KC_EQ;
+    LAUNCH(this, cls, gkr::k_eq_small, (int)(2 * n_q), 256, 0, d_q, bnl, nh, nl, mults ? d_mults : nullptr, hi, lo);
+    const int grid = grid_for(n, 256, n_sm * 8);
+    LAUNCH(this, cls, gkr::k_eq_expand, grid, 256, 0, hi, lo, nh, nl, (int)n_q, out, n);
+    CUDA_TRY(cudaGetLastError());
+    // the staging buffer is reused by the next call: make sure the copies above are done
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-GPU exchange
+// Single GPU: the kernel already published into h_result.  Sharded: all-gather the per-rank partials over
+// NCCL/NVLink, sum them modulo q on the device and publish.  Then wait and copy `nacc` elements to out.
+int gkrb200_ctx::exchange_and_fetch(int nacc, H::Fr* out) {
+    if (eff_world() > 1) {
+        const double t0 = now_ms();
+        NCCL_TRY(g_nccl.AllGather(d_local, d_all, (size_t)nacc * sizeof(FrRaw), ncclUint8, comm, stream));
+        st.launches_total++;
+        st.launches[KC_MISC]++;
+        gkr::k_sum_ranks<<<1, 32, 0, stream>>>(d_all, world, nacc, h_result, h_flag, seq);
+        st.comm_ms += now_ms() - t0;
+    }
+    TRY(wait_flag(seq));
+    memcpy(out, (const void*)h_result, (size_t)nacc * sizeof(H::Fr));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ host tail (multi-GPU residual)
+// The last log2(world) rounds run on the gathered world-entry tables: at most 4 pairs.
+static void host_round_eval(const H::Fr* eq, const H::Fr* x0, const H::Fr* x1, size_t len, int gate, const H::Fr& ark, H::Fr* evals) {
+    const int nev = gate == gkr::GATE_CIPHER ? 9 : 3;
+    const size_t mid = len / 2;
+    for (int t = 0; t < nev; t++) evals[t] = H::zero();
+    for (size_t x = 0; x < mid; x++) {
+        H::Fr e = eq[x], de = H::sub(eq[x + mid], eq[x]);
+        H::Fr s = x0[x], ds = H::sub(x0[x + mid], x0[x]);
+        if (gate == gkr::GATE_CIPHER) {
+            s = H::add(H::add(x1[x], ark), s);
+            H::Fr s1 = H::add(H::add(x1[x + mid], ark), x0[x + mid]);
+            ds = H::sub(s1, s);
+        }
+        for (int t = 0; t < nev; t++) {
+            H::Fr g = s;
+            if (gate == gkr::GATE_CIPHER) {
+                H::Fr t2 = H::sqr(s);
+                g = H::mul(H::sqr(H::mul(t2, s)), s);
+            }
+            evals[t] = H::add(evals[t], H::mul(e, g));
+            e = H::add(e, de);
+            s = H::add(s, ds);
+        }
+    }
+}
+static void host_fold(H::Fr* t, size_t len, const H::Fr& r) {
+    const size_t mid = len / 2;
+    for (size_t i = 0; i < mid; i++) t[i] = H::add(t[i], H::mul(r, H::sub(t[i + mid], t[i])));
+}
+
+// ------------------------------------------------------------------------------------------------ sumcheck.Prove
+// x0/x1: device tables of this rank (n_local = 2^(bn_total - log_world) entries when use_shards), never modified.
+// qprimes: n_q * bn_total.  Returns bn_total*(nev) coefficients, bn_total challenges, 1+arity final claims.
+int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr* qprimes, size_t n_q, const H::Fr* claims, size_t n_claims,
+                          int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out) {
+    // sumcheck/prover.go:113-115
+    if (n_claims != n_q && n_q > 1)
+        return fail(GKRB200_ERR_ARG, "provided a multi-instance %zu but the number of claims does not match %zu", n_q, n_claims);
+    const int W = use_shards ? world : 1, LW = use_shards ? log_world : 0;
+    const int bnl = bn - LW;  // rounds run on the device
+    const int nev = gate == gkr::GATE_CIPHER ? 9 : 3;
+    const int nin = gate == gkr::GATE_CIPHER ? 2 : 1;
+    const size_t n_local = (size_t)1 << bnl;
+
+    // ---- makeEqTable (sumcheck/prover.go:102-144)
+    std::vector<H::Fr> mults;
+    bool have_mults = false;
+    if (n_q > 1 || W > 1) {
+        mults.assign(n_q, H::one());
+        have_mults = true;
+        if (n_claims >= 1 && n_q > 1) {
+            const double t0 = now_ms();
+            const H::Fr rho = H::mimc_hash(claims, n_claims);  // prover.go:128
+            st.transcript_ms += now_ms() - t0;
+            H::Fr m = rho;
+            for (size_t j = 1; j < n_q; j++) {
+                mults[j] = m;
+                m = H::mul(m, rho);
+            }
+        }
+        if (W > 1) {
+            // this rank's slice of eq(q_j, .) carries the factor of its fixed low address bits:
+            // global index = j*W + rank, address bit b of rank pairs with q[bn-1-b]
+            for (size_t j = 0; j < n_q; j++) {
+                const H::Fr* q = qprimes + j * (size_t)bn;
+                H::Fr s = mults[j];
+                for (int b = 0; b < LW; b++) {
+                    const H::Fr& qb = q[bn - 1 - b];
+                    s = H::mul(s, ((rank >> b) & 1) ? qb : H::sub(H::one(), qb));
+                }
+                mults[j] = s;
+            }
+        }
+    }
+    {
+        // local table over the first bnl variables of every q_j
+        std::vector<H::Fr> ql;
+        const H::Fr* qsrc = qprimes;
+        if (LW > 0) {
+            ql.resize(n_q * (size_t)bnl);
+            for (size_t j = 0; j < n_q; j++) memcpy(&ql[j * (size_t)bnl], qprimes + j * (size_t)bn, (size_t)bnl * sizeof(H::Fr));
+            qsrc = ql.data();
+        }
+        TRY(build_eq(qsrc, n_q, bnl, have_mults ? mults.data() : nullptr, eq));
+        CUDA_TRY(cudaStreamSynchronize(stream));  // h_stage / ql may be reused
+    }
+
+    // ---- rounds on the device
+    const FrRaw* cur[3] = {eq, x0, x1};
+    FrRaw* dstp[3] = {scratch[0], scratch[1], scratch[2]};
+    size_t len = n_local;
+    H::Fr evals[MAX_EV], r = H::zero();
+    FrRaw* result_dev = W > 1 ? d_local : h_result;
+    for (int k = 0; k < bnl; k++) {
+        gkr::RoundArgs a{};
+        const bool do_fold = k > 0;
+        const size_t half = len / (do_fold ? 4 : 2);
+        for (int i = 0; i < 3; i++) {
+            a.src[i] = cur[i];
+            a.dst[i] = dstp[i];
+        }
+        a.half = half;
+        memcpy(&a.r, &r, 32);
+        memcpy(&a.ark, &ark, 32);
+        ++seq;
+        a.red.partials = partials;
+        a.red.ticket = ticket;
+        a.red.result = result_dev;
+        a.red.flag = W > 1 ? nullptr : h_flag;
+        a.red.seq = seq;
+        const int grid = grid_for(half, ROUND_BLOCK, max_grid);
+        const size_t smem = (size_t)nev * 8 * ROUND_BLOCK * 4;
+        if (gate == gkr::GATE_CIPHER) {
+            auto kf = do_fold ? gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK> : gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK>;
+            LAUNCH(this, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
+            st.fr_mul_round += (uint64_t)half * (45 + (do_fold ? 6 : 0));
+            st.bytes_round += (uint64_t)half * 32 * (do_fold ? (12 + 6) : 6);
+        } else {
+            auto kf = do_fold ? gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK>;
+            LAUNCH(this, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
+            st.fr_mul_round += (uint64_t)half * (3 + (do_fold ? 4 : 0));
+            st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
+        }
+        CUDA_TRY(cudaGetLastError());
+        if (do_fold) {
+            for (int i = 0; i < 3; i++) cur[i] = dstp[i];
+            len /= 2;
+        }
+        TRY(exchange_and_fetch(nev, evals));
+        const double t0 = now_ms();
+        H::Fr* coeffs = proof_out + (size_t)k * nev;
+        lagrange.interpolate(evals, nev, coeffs);  // poly/lagrange.go:96
+        r = H::mimc_hash(coeffs, nev);             // common/challenge.go:10
+        challenges_out[k] = r;
+        st.transcript_ms += now_ms() - t0;
+        st.rounds++;
+    }
+    // ---- last fold on the device: tables of length 2 -> the rank's residual entries [eq, x0, x1]
+    H::Fr resid[3];
+    if (bnl > 0) {
+        gkr::FoldArgs f{};
+        f.n_tables = 1 + nin;
+        for (int i = 0; i < 1 + nin; i++) {
+            f.src[i] = cur[i];
+            f.dst[i] = d_local + 8 + i;
+        }
+        f.half = 1;
+        memcpy(&f.r, &r, 32);
+        LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 32, 0, f);
+        CUDA_TRY(cudaMemcpyAsync(h_stage, d_local + 8, (1 + nin) * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        memcpy(resid, h_stage, (1 + nin) * sizeof(H::Fr));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(h_stage, eq, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(h_stage + 1, x0, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        if (nin > 1) CUDA_TRY(cudaMemcpyAsync(h_stage + 2, x1, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        memcpy(resid, h_stage, (1 + nin) * sizeof(H::Fr));
+    }
+    if (W == 1) {
+        for (int i = 0; i < 1 + nin; i++) final_out[i] = resid[i];
+        return 0;
+    }
+    // ---- sharded: gather the residual world-entry tables (entry g = rank g's value) and finish on the host
+    {
+        const double t0 = now_ms();
+        memcpy(h_stage, resid, 3 * sizeof(H::Fr));
+        TRY(upload(d_local, h_stage, 3));
+        NCCL_TRY(g_nccl.AllGather(d_local, d_all, 3 * sizeof(FrRaw), ncclUint8, comm, stream));
+        CUDA_TRY(cudaMemcpyAsync(h_stage + 4, d_all, (size_t)W * 3 * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        st.comm_ms += now_ms() - t0;
+    }
+    H::Fr te[8], t0v[8], t1v[8];
+    for (int g = 0; g < W; g++) {
+        te[g] = h_stage[4 + 3 * g];
+        t0v[g] = h_stage[4 + 3 * g + 1];
+        t1v[g] = h_stage[4 + 3 * g + 2];
+    }
+    size_t rl = (size_t)W;
+    for (int k = bnl; k < bn; k++) {
+        const double t0 = now_ms();
+        host_round_eval(te, t0v, t1v, rl, gate, ark, evals);
+        H::Fr* coeffs = proof_out + (size_t)k * nev;
+        lagrange.interpolate(evals, nev, coeffs);
+        r = H::mimc_hash(coeffs, nev);
+        challenges_out[k] = r;
+        host_fold(te, rl, r);
+        host_fold(t0v, rl, r);
+        if (nin > 1) host_fold(t1v, rl, r);
+        rl /= 2;
+        st.transcript_ms += now_ms() - t0;
+        st.rounds++;
+    }
+    final_out[0] = te[0];
+    final_out[1] = t0v[0];
+    if (nin > 1) final_out[2] = t1v[0];
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ circuit description
+// examples/mimc.go:10-37: layer 2 = Identity(0); layer i+3 = Cipher(Arks[i])(2, i == 0 ? 1 : i+2)
+static int layer_in(int layer, int in[2]) {
+    if (layer < 2) return 0;
+    if (layer == 2) {
+        in[0] = 0;
+        return 1;
+    }
+    in[0] = 2;
+    in[1] = layer == 3 ? 1 : layer - 1;
+    return 2;
+}
+// circuit/circuit.go:28-44 BuildCircuit: number of consumers of each layer and the position of a consumer in Out
+static int n_out(int layer) { return layer == 2 ? 91 : (layer == N_LAYERS - 1 ? 0 : 1); }
+static int pos_in_out(int producer, int consumer) { return producer == 2 ? consumer - 3 : 0; }
+static int n_coeffs(int layer) { return layer < 2 ? 0 : (layer == 2 ? 3 : 9); }
+
+extern "C" size_t gkrb200_proof_vec_len(int bn) { return (size_t)1006 * (size_t)bn + 183; }
+
+extern "C" int gkrb200_gkr_prove_mimc(gkrb200_ctx* c, const uint64_t* qprime, int bn, uint64_t* proof_vec_out, uint32_t flags) {
+    if (!c || !proof_vec_out || (bn > 0 && !qprime)) return fail(GKRB200_ERR_ARG, "null argument");
+    if (c->bn < 0) return fail(GKRB200_ERR_STATE, "gkr_prove_mimc called before mimc_assign");
+    if (bn != c->bn) return fail(GKRB200_ERR_ARG, "inconsistent sizes : bn is %d but the assignment has 2^%d entries", bn, c->bn);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t ubn = (size_t)bn;
+    // gkr.Proof (gkr/prover.go:14-18) laid out per layer
+    std::vector<std::vector<H::Fr>> sc(N_LAYERS), claims(N_LAYERS), qps(N_LAYERS);
+    for (int l = 0; l < N_LAYERS; l++) {
+        sc[l].assign(ubn * (size_t)n_coeffs(l), H::zero());
+        claims[l].assign((size_t)n_out(l), H::zero());
+        qps[l].assign((size_t)(l == N_LAYERS - 1 ? 1 : n_out(l)) * ubn, H::zero());
+    }
+    if (bn) memcpy(qps[N_LAYERS - 1].data(), qprime, ubn * sizeof(H::Fr));  // prover.go:31
+    std::vector<H::Fr> challenges(ubn + 1);
+    for (int layer = N_LAYERS - 1; layer >= 0; layer--) {
+        int in[2];
+        const int k = layer_in(layer, in);
+        if (k == 0) break;  // input layer: the proof is complete (prover.go:35-39)
+        const int gate = layer == 2 ? gkr::GATE_IDENTITY : gkr::GATE_CIPHER;
+        const H::Fr ark = layer > 2 ? H::ARKS[layer - 3] : H::zero();
+        const size_t n_q = layer == N_LAYERS - 1 ? 1 : (size_t)n_out(layer);
+        const size_t n_cl = layer == N_LAYERS - 1 ? 0 : (size_t)n_out(layer);  // Claims[93] is nil (prover.go:27)
+        H::Fr fin[3];
+        TRY(c->sumcheck(c->slot(in[0]), k > 1 ? c->slot(in[1]) : nullptr, bn, qps[layer].data(), n_q, claims[layer].data(), n_cl, gate, ark,
+                        c->sharded, sc[layer].data(), challenges.data(), fin));
+        for (int i = 0; i < k; i++) {  // prover.go:66-90
+            const int at = pos_in_out(in[i], layer);
+            claims[in[i]][(size_t)at] = fin[1 + i];
+            if (bn) memcpy(&qps[in[i]][(size_t)at * ubn], challenges.data(), ubn * sizeof(H::Fr));
+        }
+    }
+    // GkrProofToVec order (prover/gadget/hints.go:236-271)
+    H::Fr* out = (H::Fr*)proof_vec_out;
+    size_t cur = 0;
+    for (int l = 0; l < N_LAYERS; l++) { if (!sc[l].empty()) memcpy(out + cur, sc[l].data(), sc[l].size() * 32); cur += sc[l].size(); }
+    for (int l = 0; l < N_LAYERS; l++) { if (!claims[l].empty()) memcpy(out + cur, claims[l].data(), claims[l].size() * 32); cur += claims[l].size(); }
+    for (int l = 0; l < N_LAYERS; l++) { if (!qps[l].empty()) memcpy(out + cur, qps[l].data(), qps[l].size() * 32); cur += qps[l].size(); }
+    if (cur != gkrb200_proof_vec_len(bn)) return fail(GKRB200_ERR_STATE, "internal: proof vector length %zu != %zu", cur, gkrb200_proof_vec_len(bn));
+    if (flags & GKRB200_PROOF_REGULAR)
+        for (size_t i = 0; i < cur; i++) out[i] = H::from_mont(out[i]);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ sumcheck.Prove on host tables
+extern "C" int gkrb200_sumcheck_prove(gkrb200_ctx* c, const uint64_t* X0, const uint64_t* X1, int bn, const uint64_t* qprimes, size_t n_q,
+                                      const uint64_t* claims, size_t n_claims, int gate_kind, const uint64_t* ark, uint64_t* proof_out,
+                                      uint64_t* challenges_out, uint64_t* final_claims_out) {
+    if (!c || !X0 || bn < 0 || n_q < 1 || (bn > 0 && !qprimes) || !final_claims_out) return fail(GKRB200_ERR_ARG, "bad argument");
+    if (gate_kind != GKRB200_GATE_IDENTITY && gate_kind != GKRB200_GATE_CIPHER)
+        return fail(GKRB200_ERR_ARG, "gate kind %d cannot cross the ABI (only IdentityGate and CipherGate)", gate_kind);
+    if (gate_kind == GKRB200_GATE_CIPHER && !X1) return fail(GKRB200_ERR_ARG, "cipher gate needs two input tables");
+    if (bn > c->max_bn) return fail(GKRB200_ERR_OOM, "table 2^%d exceeds the context capacity 2^%d", bn, c->max_bn);
+    if (n_claims && !claims) return fail(GKRB200_ERR_ARG, "null claims");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t n = (size_t)1 << bn;
+    FrRaw* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 2 * n * sizeof(FrRaw)));
+    int rc = c->upload(d, X0, n);
+    if (!rc && gate_kind == GKRB200_GATE_CIPHER) rc = c->upload(d + n, X1, n);
+    H::Fr a = H::zero();
+    if (ark) memcpy(&a, ark, 32);
+    if (!rc)
+        rc = c->sumcheck(d, gate_kind == GKRB200_GATE_CIPHER ? d + n : nullptr, bn, (const H::Fr*)qprimes, n_q, (const H::Fr*)claims, n_claims,
+                         gate_kind, a, false, (H::Fr*)proof_out, (H::Fr*)challenges_out, (H::Fr*)final_claims_out);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ building blocks
+extern "C" int gkrb200_eq_table(gkrb200_ctx* c, const uint64_t* qprimes, size_t n_q, int bn, const uint64_t* multipliers, uint64_t* out) {
+    if (!c || !out || bn < 0 || (bn > 0 && !qprimes)) return fail(GKRB200_ERR_ARG, "bad argument");
+    if (bn > c->max_bn) return fail(GKRB200_ERR_OOM, "table 2^%d exceeds the context capacity 2^%d", bn, c->max_bn);
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(c->build_eq((const H::Fr*)qprimes, n_q, bn, (const H::Fr*)multipliers, c->eq));
+    CUDA_TRY(cudaMemcpyAsync(out, c->eq, ((size_t)1 << bn) * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gkrb200_fold(gkrb200_ctx* c, const uint64_t* table, size_t n, const uint64_t* r, uint64_t* out) {
+    int bn;
+    TRY(check_n(c, n, &bn));
+    if (!table || !r || !out || n < 2) return fail(GKRB200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    FrRaw* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (n + n / 2) * sizeof(FrRaw)));
+    int rc = c->upload(d, table, n);
+    if (!rc) {
+        gkr::FoldArgs f{};
+        f.n_tables = 1;
+        f.src[0] = d;
+        f.dst[0] = d + n;
+        f.half = n / 2;
+        memcpy(&f.r, r, 32);
+        LAUNCH(c, KC_FOLD, gkr::k_fold, grid_for(n / 2, 256, c->n_sm * 8), 256, 0, f);
+        cudaError_t e = cudaMemcpyAsync(out, d + n, (n / 2) * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(GKRB200_ERR_CUDA, "fold: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int gkrb200_round_eval(gkrb200_ctx* c, const uint64_t* eq, const uint64_t* X0, const uint64_t* X1, size_t n, int gate_kind,
+                                  const uint64_t* ark, uint64_t* evals_out) {
+    int bn;
+    TRY(check_n(c, n, &bn));
+    if (!eq || !X0 || !evals_out || n < 2) return fail(GKRB200_ERR_ARG, "bad argument");
+    if (gate_kind != GKRB200_GATE_IDENTITY && gate_kind != GKRB200_GATE_CIPHER) return fail(GKRB200_ERR_ARG, "bad gate kind %d", gate_kind);
+    if (gate_kind == GKRB200_GATE_CIPHER && !X1) return fail(GKRB200_ERR_ARG, "cipher gate needs two input tables");
+    CUDA_TRY(cudaSetDevice(c->device));
+    FrRaw* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(FrRaw)));
+    int rc = c->upload(d, eq, n);
+    if (!rc) rc = c->upload(d + n, X0, n);
+    if (!rc && gate_kind == GKRB200_GATE_CIPHER) rc = c->upload(d + 2 * n, X1, n);
+    if (!rc) {
+        gkr::RoundArgs a{};
+        a.src[0] = d;
+        a.src[1] = d + n;
+        a.src[2] = d + 2 * n;
+        a.half = n / 2;
+        if (ark) memcpy(&a.ark, ark, 32);
+        ++c->seq;
+        a.red.partials = c->partials;
+        a.red.ticket = c->ticket;
+        a.red.result = c->h_result;
+        a.red.flag = c->h_flag;
+        a.red.seq = c->seq;
+        const int nev = gate_kind == GKRB200_GATE_CIPHER ? 9 : 3;
+        const int grid = grid_for(a.half, ROUND_BLOCK, c->max_grid);
+        const size_t smem = (size_t)nev * 8 * ROUND_BLOCK * 4;
+        auto kf = gate_kind == GKRB200_GATE_CIPHER ? gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK>;
+        LAUNCH(c, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
+        rc = c->wait_flag(c->seq);
+        if (!rc) memcpy(evals_out, (const void*)c->h_result, (size_t)nev * 32);
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int gkrb200_fr_batch(gkrb200_ctx* c, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+    if (!c || !a || !out || op < 0 || op > 3 || (op != 3 && !b) || n == 0) return fail(GKRB200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    FrRaw* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(FrRaw)));
+    int rc = c->upload(d, a, n);
+    if (!rc && b) rc = c->upload(d + n, b, n);
+    if (!rc) {
+        LAUNCH(c, KC_MISC, gkr::k_fr_batch, grid_for(n, 256, c->n_sm * 8), 256, 0, op, d, d + n, d + 2 * n, n);
+        cudaError_t e = cudaMemcpyAsync(out, d + 2 * n, n * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(GKRB200_ERR_CUDA, "fr_batch: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------------ host transcript pieces
+extern "C" int gkrb200_mimc_hash(const uint64_t* in, size_t n, uint64_t* out) {
+    if (!out || (n && !in)) return fail(GKRB200_ERR_ARG, "null argument");
+    H::Fr r = H::mimc_hash((const H::Fr*)in, n);
+    memcpy(out, &r, 32);
+    return 0;
+}
+extern "C" int gkrb200_interpolate(const uint64_t* evals, size_t n, uint64_t* coeffs_out) {
+    static const H::Lagrange lag;
+    if (!evals || !coeffs_out || n < 1 || n > (size_t)H::Lagrange::MAX_DOMAIN) return fail(GKRB200_ERR_ARG, "domain size %zu unsupported (1..12)", n);
+    H::Fr tmp[H::Lagrange::MAX_DOMAIN];
+    lag.interpolate((const H::Fr*)evals, (int)n, tmp);
+    memcpy(coeffs_out, tmp, n * 32);
+    return 0;
+}
+extern "C" int gkrb200_to_montgomery(const uint64_t* in, size_t n, uint64_t* out) {
+    if (n && (!in || !out)) return fail(GKRB200_ERR_ARG, "null argument");
+    for (size_t i = 0; i < n; i++) {
+        H::Fr v;
+        memcpy(&v, in + 4 * i, 32);
+        v = H::to_mont(v);
+        memcpy(out + 4 * i, &v, 32);
+    }
+    return 0;
+}
+extern "C" int gkrb200_from_montgomery(const uint64_t* in, size_t n, uint64_t* out) {
+    if (n && (!in || !out)) return fail(GKRB200_ERR_ARG, "null argument");
+    for (size_t i = 0; i < n; i++) {
+        H::Fr v;
+        memcpy(&v, in + 4 * i, 32);
+        v = H::from_mont(v);
+        memcpy(out + 4 * i, &v, 32);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ instrumentation
+extern "C" int gkrb200_stats_reset(gkrb200_ctx* c) {
+    if (!c) return fail(GKRB200_ERR_ARG, "null context");
+    c->ev_flush();
+    memset(&c->st, 0, sizeof c->st);
+    return 0;
+}
+extern "C" int gkrb200_stats_get(gkrb200_ctx* c, gkrb200_stats* out) {
+    if (!c || !out) return fail(GKRB200_ERR_ARG, "null argument");
+    TRY(c->ev_flush());
+    *out = c->st;
+    return 0;
+}
+extern "C" int gkrb200_set_profiling(gkrb200_ctx* c, int on) {
+    if (!c) return fail(GKRB200_ERR_ARG, "null context");
+    c->ev_flush();
+    c->profiling = on != 0;
+    return 0;
+}
+
+extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind, int iters, double* rate_out, double* ms_out) {
+    if (!c || !rate_out || iters < 1 || kind < 0 || kind > 1) return fail(GKRB200_ERR_ARG, "bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int block = 256, grid = c->n_sm * 8;
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, (size_t)grid * block * 32));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {  // first rep is warm-up
+        cudaEventRecord(e0, c->stream);
+        if (kind == 0) gkr::k_bench_imad_wide<<<grid, block, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
+        else gkr::k_bench_fr_mul<<<grid, block, 0, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(GKRB200_ERR_CUDA, "microbench: %s", cudaGetErrorString(e));
+    const double ops = kind == 0 ? (double)grid * block * (double)iters * 64.0 : (double)grid * block * (double)iters * 2.0;
+    *rate_out = ops / (best * 1e-3) / 1e9;
+    if (ms_out) *ms_out = best;
+    c->st.launches_total += 4;
+    c->st.launches[KC_MISC] += 4;
+    return 0;
+}

@@ -1,0 +1,353 @@
+// Device kernels of the GKR-MiMC prover (sm_100a).  One kernel per CPU hot loop of the reference:
+//   K1 k_mimc_assign   <- Circuit.Assign / Layer.Evaluate / CipherGate.EvalBatch   (circuit/assignment.go:12-32,
+//                         circuit/circuit.go:48-64, circuit/gates/cipher.go:25-42)
+//   K2 k_eq_small + k_eq_expand <- poly.FoldedEqTable / ChunkOfEqTable             (poly/eq.go:41-89)
+//   K5 k_eq_expand (n_claims>1) <- multi-claim combination                         (sumcheck/prover.go:121-141, algo.go:219-223)
+//   K3 k_round (eval)  <- getPartialPolyChunk + consumeAccumulate                  (sumcheck/algo.go:54-205, prover.go:236-245)
+//   K4 k_round (fold) / k_fold <- MultiLin.FoldChunk                               (poly/multilin.go:26-36, sumcheck/algo.go:46-51)
+// All tables are arrays of FrRaw (Go's fr.Element image), moved with 256-bit accesses.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fr_device.cuh"
+
+namespace gkr {
+
+enum { GATE_IDENTITY = 0, GATE_CIPHER = 1 };
+
+__constant__ FrRaw c_arks[91] = {
+#include "mimc_arks.inc"
+};
+
+// ------------------------------------------------------------------------------------------------
+// Block-wide / grid-wide reduction of NACC field accumulators per thread.
+// Shared layout u32 sm[NACC][8][BLOCK] (thread index fastest => conflict-free).  Field addition is
+// exact, so the summation order is irrelevant to the result (no determinism concern).
+// ------------------------------------------------------------------------------------------------
+template <int NACC, int BLOCK>
+__device__ __forceinline__ void smem_put(uint32_t* sm, int k, int tid, const Fr& a) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) sm[(k * 8 + l) * BLOCK + tid] = a.v[l];
+}
+template <int BLOCK>
+__device__ __forceinline__ Fr smem_get(const uint32_t* sm, int k, int tid) {
+    Fr a;
+#pragma unroll
+    for (int l = 0; l < 8; l++) a.v[l] = sm[(k * 8 + l) * BLOCK + tid];
+    return a;
+}
+// tree-reduce sm[k][.][0..BLOCK) into sm[k][.][0] for every k, using all threads at every level
+template <int NACC, int BLOCK>
+__device__ __forceinline__ void smem_tree_reduce(uint32_t* sm, int tid) {
+    __syncthreads();
+#pragma unroll 1
+    for (int stride = BLOCK / 2; stride >= 1; stride >>= 1) {
+        const int items = NACC * stride;
+#pragma unroll 1
+        for (int it = tid; it < items; it += BLOCK) {
+            const int k = it / stride, i = it - k * stride;
+            Fr a = smem_get<BLOCK>(sm, k, i), b = smem_get<BLOCK>(sm, k, i + stride);
+            a = fr_add(a, b);
+#pragma unroll
+            for (int l = 0; l < 8; l++) sm[(k * 8 + l) * BLOCK + i] = a.v[l];
+        }
+        __syncthreads();
+    }
+}
+
+struct ReduceOut {
+    FrRaw* partials;         // [gridDim.x][NACC] device scratch
+    unsigned int* ticket;    // device counter, zero between launches
+    FrRaw* result;           // NACC elements; device memory or mapped pinned host memory
+    volatile uint32_t* flag; // optional: set to seq (after a system fence) once result is written
+    uint32_t seq;
+};
+
+// Every thread contributes acc[NACC]; the grid total lands in out.result (written by one thread of the last block).
+template <int NACC, int BLOCK>
+__device__ __forceinline__ void grid_reduce(const Fr (&acc)[NACC], const ReduceOut& out, uint32_t* sm) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < NACC; k++) smem_put<NACC, BLOCK>(sm, k, tid, acc[k]);
+    smem_tree_reduce<NACC, BLOCK>(sm, tid);
+    __shared__ bool is_last;
+    if (gridDim.x == 1) {
+        if (tid < NACC) fr_store(out.result + tid, smem_get<BLOCK>(sm, tid, 0));
+    } else {
+        if (tid < NACC) fr_store(out.partials + (size_t)blockIdx.x * NACC + tid, smem_get<BLOCK>(sm, tid, 0));
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        // last block: sum the per-block partials
+#pragma unroll 1
+        for (int k = 0; k < NACC; k++) {
+            Fr s = fr_zero();
+#pragma unroll 1
+            for (unsigned b = tid; b < gridDim.x; b += BLOCK) s = fr_add(s, fr_load(out.partials + (size_t)b * NACC + k));
+#pragma unroll
+            for (int l = 0; l < 8; l++) sm[(k * 8 + l) * BLOCK + tid] = s.v[l];
+        }
+        smem_tree_reduce<NACC, BLOCK>(sm, tid);
+        if (tid < NACC) fr_store(out.result + tid, smem_get<BLOCK>(sm, tid, 0));
+        if (tid == 0) *out.ticket = 0;
+    }
+    if (out.flag) {
+        if (tid < NACC) __threadfence_system();  // publish this thread's result element before the barrier
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            *out.flag = out.seq;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: batched MiMC layer assignment.  One thread = one hash; the 91 round states go to layers 3..93.
+// layers[l] for l in 3..93 is at base + (l-3)*stride.  a[2] is an alias of a[0] (IdentityGate copy).
+// Per hash: 364 Fr-mul, reads 64 B, writes 91*32 B.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_mimc_assign(const FrRaw* __restrict__ key, const FrRaw* __restrict__ msg, FrRaw* __restrict__ base,
+                                                      size_t stride, size_t n) {
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        const Fr k = fr_load_stream(key + x);
+        Fr s = fr_load_stream(msg + x);
+#pragma unroll 1
+        for (int i = 0; i < 91; i++) {
+            // examples/mimc.go:32: layer i+3 = Cipher(Arks[i])(a[2], prev) = (prev + ark + key)^7 (cipher.go:34-40)
+            Fr t = fr_add(fr_add(s, fr_unpack(c_arks[i])), k);
+            s = fr_pow7(t);
+            fr_store(base + (size_t)i * stride + x, s);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2/K5 stage 1: small eq tables by doubling (poly/eq.go:49-56), one block per (claim, half).
+// For claim j: hi_j = mult_j * eq(q_j[0:nh], .)  (2^nh entries),  lo_j = eq(q_j[nh:nh+nl], .)  (2^nl entries).
+// blockIdx.x = 2*j + (0: hi, 1: lo).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_eq_small(const FrRaw* __restrict__ qprimes, int bn, int nh, int nl, const FrRaw* __restrict__ mults,
+                                                   FrRaw* __restrict__ hi, FrRaw* __restrict__ lo) {
+    const int j = blockIdx.x >> 1, which = blockIdx.x & 1;
+    const FrRaw* q = qprimes + (size_t)j * bn + (which ? nh : 0);
+    const int nv = which ? nl : nh;
+    FrRaw* t = which ? lo + ((size_t)j << nl) : hi + ((size_t)j << nh);
+    if (threadIdx.x == 0) fr_store(t, (which == 0 && mults) ? fr_load(mults + j) : fr_one());
+    __syncthreads();
+    for (int i = 0; i < nv; i++) {
+        const Fr r = fr_load(q + i);
+        for (int jj = threadIdx.x; jj < (1 << i); jj += blockDim.x) {
+            const size_t J = (size_t)jj << (nv - i);
+            const size_t JN = J + ((size_t)1 << (nv - 1 - i));
+            const Fr a = fr_load(t + J);
+            const Fr b = fr_mul(r, a);
+            fr_store(t + JN, b);
+            fr_store(t + J, fr_sub(a, b));
+        }
+        __syncthreads();
+    }
+}
+// K2/K5 stage 2: out[x] = sum_j hi_j[x >> nl] * lo_j[x & (2^nl-1)]   (one streaming write of the table)
+__global__ void __launch_bounds__(256) k_eq_expand(const FrRaw* __restrict__ hi, const FrRaw* __restrict__ lo, int nh, int nl, int n_claims,
+                                                    FrRaw* __restrict__ out, size_t n) {
+    const size_t mask = ((size_t)1 << nl) - 1;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        Fr acc = fr_mul(fr_load(hi + (x >> nl)), fr_load(lo + (x & mask)));
+#pragma unroll 1
+        for (int j = 1; j < n_claims; j++) {
+            const Fr h = fr_load(hi + ((size_t)j << nh) + (x >> nl));
+            const Fr l = fr_load(lo + ((size_t)j << nl) + (x & mask));
+            acc = fr_add(acc, fr_mul(h, l));
+        }
+        fr_store(out + x, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4 standalone: fold NT tables: dst[i] = src[i] + r*(src[i+half] - src[i]),  i < half.
+// ------------------------------------------------------------------------------------------------
+struct FoldArgs {
+    const FrRaw* src[3];
+    FrRaw* dst[3];
+    int n_tables;
+    size_t half;
+    FrRaw r;
+};
+__global__ void __launch_bounds__(256) k_fold(const FoldArgs a) {
+    const Fr r = fr_unpack(a.r);
+    const size_t total = a.half * (size_t)a.n_tables;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / a.half);
+        const size_t x = i - (size_t)t * a.half;
+        const Fr b = fr_load_stream(a.src[t] + x);
+        const Fr u = fr_load_stream(a.src[t] + x + a.half);
+        fr_store(a.dst[t] + x, fr_add(b, fr_mul(r, fr_sub(u, b))));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3(+K4): one sumcheck round.  FOLD: first fold the source tables (length 4*half) with the previous
+// challenge r into dst (length 2*half; in place allowed), then evaluate this round's polynomial on the
+// `half` pairs (x, x+half) of the folded tables.  !FOLD: evaluate directly on src (length 2*half).
+//   evals[t] = sum_x eq_t(x) * gate(X_t(x)),  v_t(x) = v[x] + t*(v[x+half]-v[x]),  t = 0..NEV-1
+// cipher: gate = (X0 + X1 + ark)^7, NEV = 9 (45 mul/pair + 6 for the fold); identity: gate = X0, NEV = 3.
+// ------------------------------------------------------------------------------------------------
+struct RoundArgs {
+    const FrRaw* src[3];  // eq, X0, X1
+    FrRaw* dst[3];
+    size_t half;
+    FrRaw r;    // previous challenge (FOLD)
+    FrRaw ark;  // cipher gate constant
+    ReduceOut red;
+};
+
+template <int GATE>
+struct GateTraits;
+template <>
+struct GateTraits<GATE_IDENTITY> {
+    static constexpr int NIN = 1, NEV = 3;
+};
+template <>
+struct GateTraits<GATE_CIPHER> {
+    static constexpr int NIN = 2, NEV = 9;
+};
+
+template <bool FOLD>
+__device__ __forceinline__ void load_pair(const FrRaw* src, FrRaw* dst, size_t x, size_t half, const Fr& r, Fr& bot, Fr& top) {
+    if (FOLD) {
+        const size_t m = 2 * half;
+        const Fr b0 = fr_load_stream(src + x), t0 = fr_load_stream(src + x + m);
+        const Fr b1 = fr_load_stream(src + x + half), t1 = fr_load_stream(src + x + half + m);
+        bot = fr_add(b0, fr_mul(r, fr_sub(t0, b0)));
+        top = fr_add(b1, fr_mul(r, fr_sub(t1, b1)));
+        fr_store(dst + x, bot);
+        fr_store(dst + x + half, top);
+    } else {
+        bot = fr_load_stream(src + x);
+        top = fr_load_stream(src + x + half);
+    }
+}
+
+template <int GATE, bool FOLD, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_round(const RoundArgs a) {
+    constexpr int NEV = GateTraits<GATE>::NEV;
+    extern __shared__ uint32_t sm[];
+    Fr acc[NEV];
+#pragma unroll
+    for (int t = 0; t < NEV; t++) acc[t] = fr_zero();
+    const Fr r = fr_unpack(a.r);
+    const Fr ark = fr_unpack(a.ark);
+
+    for (size_t x = (size_t)blockIdx.x * BLOCK + threadIdx.x; x < a.half; x += (size_t)gridDim.x * BLOCK) {
+        Fr e0, e1, s0, s1;
+        load_pair<FOLD>(a.src[0], a.dst[0], x, a.half, r, e0, e1);
+        load_pair<FOLD>(a.src[1], a.dst[1], x, a.half, r, s0, s1);
+        if (GATE == GATE_CIPHER) {
+            Fr r0, r1;
+            load_pair<FOLD>(a.src[2], a.dst[2], x, a.half, r, r0, r1);
+            s0 = fr_add(fr_add(r0, ark), s0);  // cipher.go:34-35  tmp = vR + Ark + vL
+            s1 = fr_add(fr_add(r1, ark), s1);
+        }
+        const Fr de = fr_sub(e1, e0), ds = fr_sub(s1, s0);
+        // t = 0 and t = 1 use the table values directly (algo.go:107-147); t >= 2 by repeated addition (:149-199)
+        acc[0] = fr_add(acc[0], fr_mul(e0, GATE == GATE_CIPHER ? fr_pow7(s0) : s0));
+        acc[1] = fr_add(acc[1], fr_mul(e1, GATE == GATE_CIPHER ? fr_pow7(s1) : s1));
+        Fr e = e1, s = s1;
+#pragma unroll
+        for (int t = 2; t < NEV; t++) {
+            e = fr_add(e, de);
+            s = fr_add(s, ds);
+            acc[t] = fr_add(acc[t], fr_mul(e, GATE == GATE_CIPHER ? fr_pow7(s) : s));
+        }
+    }
+    grid_reduce<NEV, BLOCK>(acc, a.red, sm);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU helpers
+// ------------------------------------------------------------------------------------------------
+// strided shard of a full table: dst[j] = src[j*G + g]
+__global__ void __launch_bounds__(256) k_take_shard(const FrRaw* __restrict__ src, FrRaw* __restrict__ dst, size_t n_local, int G, int g) {
+    for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_local; j += (size_t)gridDim.x * blockDim.x)
+        fr_store(dst + j, fr_load_stream(src + j * (size_t)G + g));
+}
+// result[k] = sum_g all[g*nacc + k]; then raise the flag
+__global__ void k_sum_ranks(const FrRaw* __restrict__ all, int G, int nacc, FrRaw* result, volatile uint32_t* flag, uint32_t seq) {
+    const int k = threadIdx.x;
+    if (k < nacc) {
+        Fr s = fr_load(all + k);
+        for (int g = 1; g < G; g++) s = fr_add(s, fr_load(all + (size_t)g * nacc + k));
+        fr_store(result + k, s);
+    }
+    __syncthreads();
+    if (k == 0 && flag) {
+        __threadfence_system();
+        *flag = seq;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise ops for arithmetic parity tests
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fr_batch(int op, const FrRaw* __restrict__ a, const FrRaw* __restrict__ b, FrRaw* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const Fr x = fr_load(a + i);
+        Fr y = fr_zero();
+        if (op != 3) y = fr_load(b + i);
+        Fr z;
+        switch (op) {
+            case 0: z = fr_mul(x, y); break;
+            case 1: z = fr_add(x, y); break;
+            case 2: z = fr_sub(x, y); break;
+            default: z = fr_pow7(x); break;
+        }
+        fr_store(out + i, z);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integer-pipe microbenchmarks (roofline denominators)
+// ------------------------------------------------------------------------------------------------
+// kind 0: 8 independent IMAD.WIDE.U32 accumulation chains per thread
+__global__ void __launch_bounds__(256) k_bench_imad_wide(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t x = seed + threadIdx.x, y = seed * 3u + blockIdx.x;
+    uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            asm volatile(
+                "mad.wide.u32 %0, %8, %9, %0;\n\t"
+                "mad.wide.u32 %1, %8, %9, %1;\n\t"
+                "mad.wide.u32 %2, %8, %9, %2;\n\t"
+                "mad.wide.u32 %3, %8, %9, %3;\n\t"
+                "mad.wide.u32 %4, %8, %9, %4;\n\t"
+                "mad.wide.u32 %5, %8, %9, %5;\n\t"
+                "mad.wide.u32 %6, %8, %9, %6;\n\t"
+                "mad.wide.u32 %7, %8, %9, %7;"
+                : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
+                : "r"(x), "r"(y));
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+}
+// kind 1: two independent dependent-chains of fr_mul per thread (what the prover kernels look like)
+__global__ void __launch_bounds__(256) k_bench_fr_mul(FrRaw* out, int iters, uint32_t seed) {
+    Fr a = fr_one(), b = fr_one();
+    a.v[0] ^= seed + threadIdx.x;
+    b.v[1] ^= seed + blockIdx.x;
+    a = fr_reduce_once(a);
+    b = fr_reduce_once(b);
+    Fr c = b, d = a;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        a = fr_mul(a, b);
+        c = fr_mul(c, d);
+    }
+    fr_store(out + (size_t)blockIdx.x * blockDim.x + threadIdx.x, fr_add(a, c));
+}
+
+}  // namespace gkr

@@ -1,0 +1,81 @@
+"""circuit/ + examples/ of the reference: the MiMC circuit and its device-resident assignment."""
+from ._lib import check, lib
+from .context import _p, fr_array, fr_empty
+
+N_LAYERS = 94
+
+
+class Layer:
+    """circuit/circuit.go:14-23"""
+
+    def __init__(self, In, gate_kind=None):
+        self.In, self.Out, self.gate_kind = list(In), [], gate_kind
+
+
+class Assignment:
+    """circuit.Assignment (circuit/assignment.go:9): a[layer] reads the layer back from the device."""
+
+    def __init__(self, ctx, n_local, bn):
+        self.ctx, self.n_local, self.bn = ctx, n_local, bn
+
+    def __len__(self):
+        return N_LAYERS
+
+    def __getitem__(self, layer):
+        if layer < 0:
+            layer += N_LAYERS
+        out = fr_empty(self.n_local)
+        check(lib().gkrb200_assign_layer_to_host(self.ctx.handle, layer, _p(out), self.n_local))
+        return out
+
+
+class MimcCircuit:
+    """examples.MimcCircuit() (examples/mimc.go:10-37) bound to a device context."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.layers = [Layer([]), Layer([]), Layer([0], 0)]
+        for i in range(91):
+            self.layers.append(Layer([2, 1 if i == 0 else i + 2], 1))
+        for l, lay in enumerate(self.layers):  # circuit/circuit.go:28-44 BuildCircuit
+            for pos in lay.In:
+                self.layers[pos].Out.append(l)
+
+    def __len__(self):
+        return N_LAYERS
+
+    def __getitem__(self, l):
+        return self.layers[l]
+
+    def IsInputLayer(self, layer):
+        return len(self.layers[layer].In) == 0
+
+    def InputArity(self):
+        return 2
+
+    def _shape(self, n):
+        world = self.ctx.world
+        bn = n.bit_length() - 1
+        sharded = world > 1 and (1 << bn) > world
+        return bn, (n // world if sharded else n)
+
+    def Assign(self, key, msg, want_outputs=False):
+        """Circuit.Assign(inps...) (circuit/assignment.go:12-32).  key -> layer 0, msg -> layer 1."""
+        k = fr_array(key).reshape(-1, 4)
+        m = fr_array(msg).reshape(-1, 4)
+        if k.shape != m.shape:
+            raise ValueError("inputs must have the same length")
+        n = k.shape[0]
+        bn, n_local = self._shape(n)
+        out93 = fr_empty(n_local) if want_outputs else None
+        check(lib().gkrb200_mimc_assign(self.ctx.handle, _p(k), _p(m), n, _p(out93)))
+        a = Assignment(self.ctx, n_local, bn)
+        if want_outputs:
+            a.outputs = out93
+        return a
+
+    def AssignDevice(self, d_key_ptr, d_msg_ptr, n):
+        """Same with inputs already on the device (raw device pointers, Go layout); asynchronous."""
+        bn, n_local = self._shape(n)
+        check(lib().gkrb200_mimc_assign_device(self.ctx.handle, d_key_ptr, d_msg_ptr, n))
+        return Assignment(self.ctx, n_local, bn)

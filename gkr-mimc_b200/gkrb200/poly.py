@@ -1,0 +1,39 @@
+"""poly/ of the reference on the device."""
+from ._lib import check, lib
+from .context import _p, fr_array, fr_empty
+
+
+def FoldedEqTable(ctx, qPrime, multiplier=None):
+    """poly/eq.go:41-59 (also what ChunkOfEqTable :62-89 assembles)"""
+    q = fr_array(qPrime).reshape(-1, 4)
+    bn = q.shape[0]
+    out = fr_empty(1 << bn)
+    m = fr_array(multiplier).reshape(1, 4) if multiplier is not None else None
+    check(lib().gkrb200_eq_table(ctx.handle, _p(q), 1, bn, _p(m), _p(out)))
+    return out
+
+
+def MultiEqTable(ctx, qPrimes, multipliers):
+    """sum_j multipliers[j] * eq(qPrimes[j], .)  -- the combination of sumcheck/prover.go:121-141"""
+    q = fr_array(qPrimes)
+    n_q, bn = q.shape[0], q.shape[1]
+    m = fr_array(multipliers).reshape(n_q, 4)
+    out = fr_empty(1 << bn)
+    check(lib().gkrb200_eq_table(ctx.handle, _p(q), n_q, bn, _p(m), _p(out)))
+    return out
+
+
+def Fold(ctx, table, r):
+    """MultiLin.Fold (poly/multilin.go:19-36); returns the folded table (half the length)"""
+    t = fr_array(table).reshape(-1, 4)
+    out = fr_empty(t.shape[0] // 2)
+    check(lib().gkrb200_fold(ctx.handle, _p(t), t.shape[0], _p(fr_array(r)), _p(out)))
+    return out
+
+
+def InterpolateOnRange(values):
+    """poly/lagrange.go:96-111"""
+    v = fr_array(values).reshape(-1, 4)
+    out = fr_empty(v.shape[0])
+    check(lib().gkrb200_interpolate(_p(v), v.shape[0], _p(out)))
+    return out

@@ -1,0 +1,297 @@
+"""GPU parity tests: every device path through the C ABI (libgkrb200.so) against the CPU oracle.
+
+Mirrors the reference's own tests: gates_test.go, eq_test.go, multilin_test.go,
+sumcheck/prover_test.go (TestWithCipherGate, TestWithMultiIdentity, bn 0..14), gkr/gkr_test.go (TestGKR, bn 0..11),
+examples/mimc_test.go.  Integer arithmetic: the bar is bit-exact equality of every word."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+Q = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rand_fr(rng, n):
+    """n uniformly random canonical elements (Montgomery image is just another canonical element)"""
+    vals = [int.from_bytes(rng.bytes(40), "little") % Q for _ in range(n)]
+    a = np.zeros((n, 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for j in range(4):
+            a[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return a
+
+
+def edge_fr():
+    vals = [0, 1, 2, Q - 1, Q - 2, (1 << 256) % Q, (1 << 255) % Q, Q // 2, Q // 2 + 1, 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF, (1 << 128) - 1,
+            Q - (1 << 32), Q - (1 << 64), (1 << 253), (1 << 253) - 1]
+    a = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for j in range(4):
+            a[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return a
+
+
+def sha_regular(oracle, vec):
+    return hashlib.sha256(b"".join(x.to_bytes(32, "big") for x in oracle.from_mont(vec))).hexdigest()
+
+
+# ----------------------------------------------------------------------------- field arithmetic
+def test_device_field_ops_match_oracle(ctx, oracle):
+    rng = np.random.default_rng(1)
+    e = edge_fr()
+    # all edge pairs + random
+    a = np.concatenate([np.repeat(e, len(e), axis=0), rand_fr(rng, 4096)])
+    b = np.concatenate([np.tile(e, (len(e), 1)), rand_fr(rng, 4096)])
+    for op, f in ((0, oracle.fr_mul), (1, oracle.fr_add), (2, oracle.fr_sub)):
+        got = ctx.fr_batch(op, a, b)
+        exp = np.stack([f(a[i], b[i]) for i in range(a.shape[0])])
+        assert np.array_equal(got, exp), "op %d" % op
+    got = ctx.fr_batch(3, a)
+    for i in range(0, a.shape[0], 7):
+        x2 = oracle.fr_mul(a[i], a[i])
+        x3 = oracle.fr_mul(x2, a[i])
+        x6 = oracle.fr_mul(x3, x3)
+        assert np.array_equal(got[i], oracle.fr_mul(x6, a[i]))
+
+
+# ----------------------------------------------------------------------------- K1 assignment
+@pytest.mark.parametrize("bn", [0, 1, 3, 7, 12])
+def test_mimc_assign_all_layers(ctx, oracle, bn):
+    """examples/mimc_test.go:19-42 + every layer against the oracle's Assign"""
+    import gkrb200
+    n = 1 << bn
+    key, msg = oracle.random_fr_array(n), oracle.random_fr_array(n)[::-1].copy()
+    c = gkrb200.MimcCircuit(ctx)
+    a = c.Assign(key, msg, want_outputs=True)
+    exp = oracle.mimc_assign(key, msg)
+    for layer in (0, 1, 2, 3, 4, 50, 92, 93):
+        assert np.array_equal(a[layer], exp[layer]), "layer %d" % layer
+    assert np.array_equal(a.outputs, exp[93])
+    # a[93][x] == MimcKeyedPermutation(msg[x], key[x])  (examples/mimc_test.go:36-41)
+    for x in (0, n - 1):
+        assert np.array_equal(a[93][x], oracle.mimc_keyed_permutation(msg[x], key[x]))
+
+
+def test_mimc_assign_golden_output(ctx, oracle):
+    """a[93][0] for key = msg = RandomFrArray"""
+    import gkrb200
+    c = gkrb200.MimcCircuit(ctx)
+    arr = gkrb200.common.RandomFrArray(8)
+    a = c.Assign(arr, arr)
+    assert oracle.from_mont(a[93][0])[0] == 8841465970847011079291916190149068638245134784377117452947505492959099071201
+
+
+# ----------------------------------------------------------------------------- K2 eq table
+@pytest.mark.parametrize("bn", list(range(0, 15)))
+def test_eq_table_matches_oracle_and_closed_form(ctx, oracle, bn):
+    """poly/eq_test.go:12-58"""
+    import gkrb200
+    q = oracle.random_fr_array(bn + 3)[3:]
+    got = gkrb200.poly.FoldedEqTable(ctx, q)
+    assert np.array_equal(got, oracle.folded_eq_table(q))
+    if bn >= 8:
+        assert np.array_equal(got, oracle.chunked_eq_table(q, 256))
+    if bn:
+        h = oracle.random_fr_array(bn)
+        assert np.array_equal(oracle.evaluate(got, h), oracle.eval_eq(q, h))
+    m = oracle.random_fr_array(5)[4]
+    assert np.array_equal(gkrb200.poly.FoldedEqTable(ctx, q, m), oracle.folded_eq_table(q, m))
+
+
+@pytest.mark.parametrize("bn,n_q", [(0, 3), (1, 2), (5, 10), (9, 91), (12, 91)])
+def test_multi_eq_table(ctx, oracle, bn, n_q):
+    """K5: sum_j rho^j eq(q_j, .) against makeEqTable (sumcheck/prover.go:102-144)"""
+    import gkrb200
+    rng = np.random.default_rng(bn * 100 + n_q)
+    qs = rand_fr(rng, n_q * bn).reshape(n_q, bn, 4)
+    claims = rand_fr(rng, n_q)
+    exp, rho = oracle.make_eq_table(claims, qs)
+    mults = [oracle.to_mont([1])[0]]
+    for j in range(1, n_q):
+        mults.append(rho if j == 1 else oracle.fr_mul(mults[-1], rho))
+    got = gkrb200.poly.MultiEqTable(ctx, qs, np.stack(mults))
+    assert np.array_equal(got, exp)
+
+
+# ----------------------------------------------------------------------------- K4 fold
+def test_fold_golden(ctx, oracle):
+    """poly/multilin_test.go:12-31: [0,1,2,3].Fold(5) == [10,11]"""
+    import gkrb200
+    t = gkrb200.common.SetUint64([0, 1, 2, 3])
+    r = gkrb200.common.SetUint64([5])[0]
+    got = gkrb200.poly.Fold(ctx, t, r)
+    assert oracle.from_mont(got) == [10, 11]
+
+
+@pytest.mark.parametrize("bn", [1, 2, 5, 10, 14, 16])
+def test_fold_random(ctx, oracle, bn):
+    import gkrb200
+    rng = np.random.default_rng(bn)
+    t, r = rand_fr(rng, 1 << bn), rand_fr(rng, 1)[0]
+    assert np.array_equal(gkrb200.poly.Fold(ctx, t, r), oracle.fold(t, r))
+
+
+# ----------------------------------------------------------------------------- K3 round evaluation
+@pytest.mark.parametrize("bn", [1, 2, 4, 8, 11, 13])
+def test_round_eval_cipher(ctx, oracle, bn):
+    import gkrb200
+    rng = np.random.default_rng(bn)
+    n = 1 << bn
+    eq, L, R = rand_fr(rng, n), rand_fr(rng, n), rand_fr(rng, n)
+    ark = rand_fr(rng, 1)[0]
+    got = gkrb200.sumcheck.PartialEvals(ctx, eq, [L, R], gkrb200.gates.CipherGate(ark))
+    assert np.array_equal(got, oracle.partial_evals(eq, L, R, oracle.GATE_CIPHER, ark))
+
+
+@pytest.mark.parametrize("bn", [1, 3, 9, 13])
+def test_round_eval_identity(ctx, oracle, bn):
+    import gkrb200
+    rng = np.random.default_rng(bn)
+    n = 1 << bn
+    eq, L = rand_fr(rng, n), rand_fr(rng, n)
+    got = gkrb200.sumcheck.PartialEvals(ctx, eq, [L], gkrb200.gates.IdentityGate())
+    assert np.array_equal(got, oracle.partial_evals(eq, L, None, oracle.GATE_IDENTITY))
+
+
+# ----------------------------------------------------------------------------- sumcheck.Prove
+def _check_sumcheck(ctx, oracle, X, claims, qs, gate, okind, ark):
+    import gkrb200
+    proof, chal, fin = gkrb200.sumcheck.Prove(ctx, X, qs, claims, gate)
+    eproof, echal, efin = oracle.sumcheck_prove(X, qs, claims, okind, ark)
+    assert np.array_equal(proof, eproof)
+    assert np.array_equal(chal, echal)
+    assert np.array_equal(fin, efin)
+    # sumcheck/prover_test.go:59-77: the verifier accepts and agrees on the challenges
+    rc, vchal, vfin, _ = oracle.sumcheck_verify(claims, proof)
+    assert rc == 0
+    assert np.array_equal(vchal, chal)
+
+
+@pytest.mark.parametrize("bn", list(range(0, 15)))
+def test_sumcheck_cipher_gate(ctx, oracle, bn):
+    """sumcheck/prover_test.go:88-94 TestWithCipherGate with InitializeCipherGateInstance (testing.go:11-26)"""
+    import gkrb200
+    n = 1 << bn
+    q = oracle.random_fr_array(bn).reshape(1, bn, 4)
+    ark = gkrb200.common.SetUint64([145646])[0]
+    L = gkrb200.common.SetUint64(range(n))
+    claim = oracle.evaluation(oracle.GATE_CIPHER, ark, q, None, L, L)
+    _check_sumcheck(ctx, oracle, [L, L.copy()], claim.reshape(1, 4), q, gkrb200.gates.CipherGate(ark), oracle.GATE_CIPHER, ark)
+
+
+@pytest.mark.parametrize("bn,ninst", [(b, 10) for b in range(0, 15)] + [(6, 91), (11, 91)])
+def test_sumcheck_multi_identity(ctx, oracle, bn, ninst):
+    """sumcheck/prover_test.go:80-86 TestWithMultiIdentity with InitializeMultiInstance (testing.go:28-57)"""
+    import gkrb200
+    n = 1 << bn
+    qs = np.stack([gkrb200.common.SetUint64([i * j + i for j in range(bn)]).reshape(bn, 4) for i in range(ninst)])
+    L = gkrb200.common.SetUint64(range(n))
+    claims = np.stack([oracle.evaluation(oracle.GATE_IDENTITY, None, qs[i:i + 1], None, L) for i in range(ninst)])
+    _check_sumcheck(ctx, oracle, [L], claims, qs, gkrb200.gates.IdentityGate(), oracle.GATE_IDENTITY, None)
+
+
+def test_sumcheck_golden_digests(ctx, oracle):
+    """tests/golden/sumcheck_cipher.json: claim, sha256 of the round coefficients, first challenge (bn 1..4)"""
+    import gkrb200
+    gold = json.load(open(os.path.join(GOLDEN, "sumcheck_cipher.json")))
+    for bn_s, g in gold.items():
+        bn = int(bn_s)
+        n = 1 << bn
+        q = oracle.random_fr_array(bn).reshape(1, bn, 4)
+        ark = gkrb200.common.SetUint64([145646])[0]
+        L = gkrb200.common.SetUint64(range(n))
+        claim = gkrb200.common.ToMontgomery(np.array([[(int(g["claim"]) >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)]], dtype=np.uint64))
+        proof, chal, _ = gkrb200.sumcheck.Prove(ctx, [L, L], q, claim, gkrb200.gates.CipherGate(ark))
+        assert sha_regular(oracle, proof.reshape(-1, 4)) == g["sha256_coeffs"]
+        assert str(oracle.from_mont(chal[0])[0]) == g["first_challenge"]
+
+
+def test_sumcheck_rejects_bad_arguments(ctx, oracle):
+    """the reference panics (sumcheck/prover.go:54, :114); the ABI returns an error and the binding raises"""
+    import gkrb200
+    L = gkrb200.common.SetUint64(range(8))
+    q2 = oracle.random_fr_array(6).reshape(2, 3, 4)
+    with pytest.raises(gkrb200.GkrB200Error):
+        gkrb200.sumcheck.Prove(ctx, [L], q2, oracle.random_fr_array(1), gkrb200.gates.IdentityGate())  # 2 qPrimes, 1 claim
+    with pytest.raises(ValueError):
+        gkrb200.sumcheck.Prove(ctx, [L[:4]], q2[:1], None, gkrb200.gates.IdentityGate())  # table size != 2^bn
+    with pytest.raises(gkrb200.GkrB200Error):
+        gkrb200.poly.Fold(ctx, oracle.random_fr_array(6), L[0])  # not a power of two
+    big = np.zeros((1 << 17, 4), dtype=np.uint64)
+    with pytest.raises(gkrb200.GkrB200Error):
+        gkrb200.MimcCircuit(ctx).Assign(big, big)  # larger than the arena (poly/pool.go:70-72 analogue)
+
+
+# ----------------------------------------------------------------------------- gkr.Prove
+@pytest.mark.parametrize("bn", list(range(0, 12)))
+def test_gkr_prove_matches_oracle_and_verifies(ctx, oracle, bn):
+    """gkr/gkr_test.go:14-78 TestGKR, inputs as :23-25; every word of the flat proof vector against the oracle"""
+    import gkrb200
+    n = 1 << bn
+    block = gkrb200.common.RandomFrArray(n)
+    qprime = gkrb200.common.RandomFrArray(bn)
+    c = gkrb200.MimcCircuit(ctx)
+    a = c.Assign(block, block)
+    proof = gkrb200.gkr.Prove(c, a, qprime)
+    out93, evec = oracle.assign_and_prove_mimc(block, block, qprime)
+    assert np.array_equal(a[93], out93)
+    assert np.array_equal(proof.to_vec(), evec)
+    assert oracle.gkr_verify_mimc(proof.to_vec(), block, block, out93, qprime) == 0
+    # claims are consistent with the (untouched) assignment: gkr_test.go:35-45
+    for layer in (0, 1, 2, 40, 92):
+        for j in range(0, len(proof.Claims[layer]), 17):
+            assert np.array_equal(proof.Claims[layer][j], oracle.evaluate(a[layer], proof.QPrimes[layer][j]))
+    # the assignment survives the proof (documented deviation: not consumed) and proving is repeatable
+    if bn in (3, 9):
+        assert np.array_equal(gkrb200.gkr.Prove(c, a, qprime).to_vec(), evec)
+
+
+def test_gkr_golden_digests(ctx, oracle):
+    """tests/golden/gkr_proof_digests.json: sha256 of the GkrProofToVec image (regular form, big-endian)"""
+    import gkrb200
+    gold = json.load(open(os.path.join(GOLDEN, "gkr_proof_digests.json")))
+    c = gkrb200.MimcCircuit(ctx)
+    for bn_s, digest in gold.items():
+        bn = int(bn_s)
+        block = gkrb200.common.RandomFrArray(1 << bn)
+        qprime = gkrb200.common.RandomFrArray(bn)
+        a = c.Assign(block, block)
+        reg = gkrb200.gkr.Prove(c, a, qprime, regular=True).to_vec()
+        words = b"".join(int(x[0] | (int(x[1]) << 64) | (int(x[2]) << 128) | (int(x[3]) << 192)).to_bytes(32, "big") for x in reg.tolist())
+        assert hashlib.sha256(words).hexdigest() == digest, bn
+
+
+def test_gkr_random_inputs_distinct_key_msg(ctx, oracle):
+    import gkrb200
+    rng = np.random.default_rng(7)
+    bn = 8
+    key, msg, qprime = rand_fr(rng, 1 << bn), rand_fr(rng, 1 << bn), rand_fr(rng, bn)
+    c = gkrb200.MimcCircuit(ctx)
+    a = c.Assign(key, msg)
+    vec = gkrb200.gkr.Prove(c, a, qprime).to_vec()
+    out93, evec = oracle.assign_and_prove_mimc(key, msg, qprime)
+    assert np.array_equal(vec, evec)
+    assert oracle.gkr_verify_mimc(vec, key, msg, out93, qprime) == 0
+    # a tampered proof is rejected by the oracle verifier (sanity of the acceptance check itself)
+    bad = vec.copy()
+    bad[5, 0] ^= np.uint64(1)
+    assert oracle.gkr_verify_mimc(bad, key, msg, out93, qprime) != 0
+
+
+def test_gkr_2pow16_full_size_properties(ctx, oracle):
+    """config 3 (2^16 hashes): oracle verifier accepts; claims match MLE evaluations of the assignment"""
+    import gkrb200
+    bn = 16
+    rng = np.random.default_rng(16)
+    key, msg, qprime = rand_fr(rng, 1 << bn), rand_fr(rng, 1 << bn), rand_fr(rng, bn)
+    c = gkrb200.MimcCircuit(ctx)
+    a = c.Assign(key, msg, want_outputs=True)
+    proof = gkrb200.gkr.Prove(c, a, qprime)
+    assert oracle.gkr_verify_mimc(proof.to_vec(), key, msg, a.outputs, qprime) == 0
+    assert np.array_equal(proof.Claims[1][0], oracle.evaluate(msg, proof.QPrimes[1][0]))
+    assert np.array_equal(proof.Claims[2][45], oracle.evaluate(key, proof.QPrimes[2][45]))
