@@ -85,6 +85,7 @@ enum KClass { KC_ASSIGN = 0, KC_EQ = 1, KC_ROUND = 2, KC_FOLD = 3, KC_MULTIEQ = 
 static constexpr int N_LAYERS = GKRB200_MIMC_LAYERS;
 static constexpr int MAX_CLAIMS = 91;
 static constexpr int ROUND_BLOCK = 128;
+static constexpr int ROUND_MINB = 5;  // resident blocks per SM the round kernels are compiled for
 static constexpr int MAX_EV = 9;
 
 static inline double now_ms() {
@@ -101,7 +102,7 @@ struct gkrb200_ctx {
 
     // device arena
     FrRaw* arena = nullptr;
-    FrRaw* layers = nullptr;     // [92][cap]: slot 0 = a[0] key (== a[2]), slot 1 = a[1] msg, slot s>=2 = a[s+1]
+    FrRaw* layers = nullptr;     // [93][cap]: slot 0 = a[0] key (== a[2]), slot 1 = a[1] msg, slot s>=2 = a[s+1]
     FrRaw* eq = nullptr;         // [cap]
     FrRaw* scratch[3] = {};      // [cap/2] each, contiguous
     FrRaw* hi = nullptr;         // [MAX_CLAIMS][2^ceil(max_bn/2)]
@@ -224,6 +225,7 @@ int gkrb200_ctx::wait_flag(uint32_t want) {
 }
 
 int gkrb200_ctx::upload(FrRaw* dst, const void* src, size_t n_elems) {
+    st.h2d_bytes += n_elems * sizeof(FrRaw);
     CUDA_TRY(cudaMemcpyAsync(dst, src, n_elems * sizeof(FrRaw), cudaMemcpyHostToDevice, stream));
     return 0;
 }
@@ -255,7 +257,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
         return fail(GKRB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     }
     c->n_sm = prop.multiProcessorCount;
-    c->max_grid = c->n_sm * 8;
+    c->max_grid = c->n_sm * ROUND_MINB;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -265,7 +267,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     const size_t half = c->cap / 2 > 0 ? c->cap / 2 : 1;
     const int nsmall = (max_bn + 1) / 2;
     const size_t small = (size_t)1 << nsmall;
-    size_t total = 92 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
+    size_t total = 93 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
                    (size_t)c->max_grid * MAX_EV + 16 + 8 * 16 + 64;
     cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
     if (me != cudaSuccess) {
@@ -273,7 +275,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
         return fail(GKRB200_ERR_OOM, "cudaMalloc of %.2f GiB arena failed: %s", total * 32.0 / (1 << 30), cudaGetErrorString(me));
     }
     FrRaw* p = c->arena;
-    c->layers = p; p += 92 * c->cap;
+    c->layers = p; p += 93 * c->cap;
     c->eq = p; p += c->cap;
     for (int i = 0; i < 3; i++) { c->scratch[i] = p; p += half; }
     c->hi = p; p += MAX_CLAIMS * small;
@@ -290,11 +292,11 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     *c->h_flag = 0;
     CUDA_TRY(cudaHostAlloc((void**)&c->h_stage, (size_t)MAX_CLAIMS * (max_bn + 2) * sizeof(H::Fr), cudaHostAllocDefault));
     // opt in to the dynamic shared memory the round kernels need
-    const int smem9 = 9 * 8 * ROUND_BLOCK * 4, smem3 = 3 * 8 * ROUND_BLOCK * 4;
-    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
-    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
-    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
-    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    const int smem9 = 9 * 9 * ROUND_BLOCK * 4, smem3 = 3 * 9 * ROUND_BLOCK * 4;
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     *out = c;
     return 0;
 }
@@ -381,7 +383,10 @@ extern "C" int gkrb200_mimc_assign(gkrb200_ctx* c, const uint64_t* key, const ui
         LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_msg, c->slot(1), c->n_local, c->world, c->rank);
     }
     TRY(assign_common(c, c->n_local));
-    if (out93) CUDA_TRY(cudaMemcpyAsync(out93, c->slot(93), c->n_local * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
+    if (out93) {
+        CUDA_TRY(cudaMemcpyAsync(out93, c->slot(93), c->n_local * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
+        c->st.d2h_bytes += c->n_local * sizeof(FrRaw);
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -452,6 +457,7 @@ int gkrb200_ctx::exchange_and_fetch(int nacc, H::Fr* out) {
     }
     TRY(wait_flag(seq));
     memcpy(out, (const void*)h_result, (size_t)nacc * sizeof(H::Fr));
+    st.d2h_bytes += (size_t)nacc * sizeof(H::Fr) + 4;
     return 0;
 }
 
@@ -567,14 +573,14 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         a.red.flag = W > 1 ? nullptr : h_flag;
         a.red.seq = seq;
         const int grid = grid_for(half, ROUND_BLOCK, max_grid);
-        const size_t smem = (size_t)nev * 8 * ROUND_BLOCK * 4;
+        const size_t smem = (size_t)nev * 9 * ROUND_BLOCK * 4;
         if (gate == gkr::GATE_CIPHER) {
-            auto kf = do_fold ? gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK> : gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK>;
+            auto kf = do_fold ? gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK, ROUND_MINB> : gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK, ROUND_MINB>;
             LAUNCH(this, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
             st.fr_mul_round += (uint64_t)half * (45 + (do_fold ? 6 : 0));
             st.bytes_round += (uint64_t)half * 32 * (do_fold ? (12 + 6) : 6);
         } else {
-            auto kf = do_fold ? gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK>;
+            auto kf = do_fold ? gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK, ROUND_MINB> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>;
             LAUNCH(this, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
             st.fr_mul_round += (uint64_t)half * (3 + (do_fold ? 4 : 0));
             st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
@@ -608,6 +614,7 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         CUDA_TRY(cudaMemcpyAsync(h_stage, d_local + 8, (1 + nin) * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         memcpy(resid, h_stage, (1 + nin) * sizeof(H::Fr));
+        st.d2h_bytes += (1 + nin) * sizeof(H::Fr);
     } else {
         CUDA_TRY(cudaMemcpyAsync(h_stage, eq, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(h_stage + 1, x0, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
@@ -808,8 +815,8 @@ extern "C" int gkrb200_round_eval(gkrb200_ctx* c, const uint64_t* eq, const uint
         a.red.seq = c->seq;
         const int nev = gate_kind == GKRB200_GATE_CIPHER ? 9 : 3;
         const int grid = grid_for(a.half, ROUND_BLOCK, c->max_grid);
-        const size_t smem = (size_t)nev * 8 * ROUND_BLOCK * 4;
-        auto kf = gate_kind == GKRB200_GATE_CIPHER ? gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK>;
+        const size_t smem = (size_t)nev * 9 * ROUND_BLOCK * 4;
+        auto kf = gate_kind == GKRB200_GATE_CIPHER ? gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK, ROUND_MINB> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>;
         LAUNCH(c, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
         rc = c->wait_flag(c->seq);
         if (!rc) memcpy(evals_out, (const void*)c->h_result, (size_t)nev * 32);
@@ -892,10 +899,22 @@ extern "C" int gkrb200_set_profiling(gkrb200_ctx* c, int on) {
     return 0;
 }
 
-extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind, int iters, double* rate_out, double* ms_out) {
-    if (!c || !rate_out || iters < 1 || kind < 0 || kind > 1) return fail(GKRB200_ERR_ARG, "bad argument");
+extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, double* rate_out, double* ms_out) {
+    // low byte: kind; next byte (optional): warps per SM to allow (occupancy limited through dynamic shared memory)
+    const int kind = kind_and_occ & 0xff, warps = (kind_and_occ >> 8) & 0xff;
+    if (!c || !rate_out || iters < 1 || kind < 0 || kind > 3) return fail(GKRB200_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    const int block = 256, grid = c->n_sm * 8;
+    int block = 256, grid = c->n_sm * 8;
+    size_t smem = 0;
+    if (warps && (kind == 1 || kind == 3)) {
+        block = 128;                                  // 4 warps per block
+        const int blocks_per_sm = warps / 4 > 0 ? warps / 4 : 1;
+        smem = (size_t)(220 * 1024) / blocks_per_sm;  // only blocks_per_sm blocks fit in shared memory
+        if (smem > 200 * 1024) smem = 200 * 1024;
+        grid = c->n_sm * blocks_per_sm * 2;
+        CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     void* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, (size_t)grid * block * 32));
     cudaEvent_t e0, e1;
@@ -905,7 +924,9 @@ extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind, int iters, double* r
     for (int rep = 0; rep < 4; rep++) {  // first rep is warm-up
         cudaEventRecord(e0, c->stream);
         if (kind == 0) gkr::k_bench_imad_wide<<<grid, block, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
-        else gkr::k_bench_fr_mul<<<grid, block, 0, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
+        else if (kind == 1) gkr::k_bench_fr_mul<<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
+        else if (kind == 2) gkr::k_bench_imad_wide_x<<<grid, block, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
+        else gkr::k_bench_fr_mul1<<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
         cudaEventRecord(e1, c->stream);
         cudaEventSynchronize(e1);
         float ms = 0;
@@ -917,8 +938,8 @@ extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind, int iters, double* r
     cudaEventDestroy(e1);
     cudaFree(d);
     if (e != cudaSuccess) return fail(GKRB200_ERR_CUDA, "microbench: %s", cudaGetErrorString(e));
-    const double ops = kind == 0 ? (double)grid * block * (double)iters * 64.0 : (double)grid * block * (double)iters * 2.0;
-    *rate_out = ops / (best * 1e-3) / 1e9;
+    const double per_thread_iter = kind == 0 ? 64.0 : (kind == 2 ? 64.0 : 2.0);
+    *rate_out = (double)grid * block * (double)iters * per_thread_iter / (best * 1e-3) / 1e9;
     if (ms_out) *ms_out = best;
     c->st.launches_total += 4;
     c->st.launches[KC_MISC] += 4;

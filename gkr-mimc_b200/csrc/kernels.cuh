@@ -231,39 +231,167 @@ __device__ __forceinline__ void load_pair(const FrRaw* src, FrRaw* dst, size_t x
     }
 }
 
-template <int GATE, bool FOLD, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_round(const RoundArgs a) {
-    constexpr int NEV = GateTraits<GATE>::NEV;
-    extern __shared__ uint32_t sm[];
-    Fr acc[NEV];
+// ---- lazy 288-bit accumulators in shared memory -------------------------------------------------
+// Each thread owns NEV accumulators of 9 x 32-bit limbs: sm[(t*9 + l)*BLOCK + tid].  Terms (< q < 2^254) are
+// added as plain integers without reduction (a grid holds < 2^24 terms per accumulator, so 288 bits never
+// overflow); one reduction mod q per block at the end.  Keeps the register file free for the multiplier.
+template <int BLOCK>
+__device__ __forceinline__ void wide_acc_add(uint32_t* slot /* &sm[t*9*BLOCK + tid] */, const Fr& term) {
+    uint32_t a[9];
 #pragma unroll
-    for (int t = 0; t < NEV; t++) acc[t] = fr_zero();
-    const Fr r = fr_unpack(a.r);
-    const Fr ark = fr_unpack(a.ark);
+    for (int l = 0; l < 9; l++) a[l] = slot[l * BLOCK];
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, %8, 0;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8])
+        : "r"(term.v[0]), "r"(term.v[1]), "r"(term.v[2]), "r"(term.v[3]), "r"(term.v[4]), "r"(term.v[5]), "r"(term.v[6]), "r"(term.v[7]));
+#pragma unroll
+    for (int l = 0; l < 9; l++) slot[l * BLOCK] = a[l];
+}
+// sm[k][.][i] += sm[k][.][i + stride]  as 288-bit integers
+template <int BLOCK>
+__device__ __forceinline__ void wide_pair_add(uint32_t* sm, int k, int i, int stride) {
+    uint32_t a[9], b[9];
+#pragma unroll
+    for (int l = 0; l < 9; l++) {
+        a[l] = sm[(k * 9 + l) * BLOCK + i];
+        b[l] = sm[(k * 9 + l) * BLOCK + i + stride];
+    }
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, %8, %17;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8])
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]));
+#pragma unroll
+    for (int l = 0; l < 9; l++) sm[(k * 9 + l) * BLOCK + i] = a[l];
+}
+// 288-bit integer (9 limbs) -> canonical residue:  lo + hi*2^256  mod q
+__device__ __forceinline__ Fr fr_from_wide(const uint32_t (&w)[9]) {
+    Fr lo, hi = fr_zero(), r2, raw1 = fr_zero();
+#pragma unroll
+    for (int l = 0; l < 8; l++) lo.v[l] = w[l];
+    hi.v[0] = w[8];
+    raw1.v[0] = 1;
+    // R^2 mod q
+    r2.v[0] = 0xae216da7u; r2.v[1] = 0x1bb8e645u; r2.v[2] = 0xe35c59e3u; r2.v[3] = 0x53fe3ab1u;
+    r2.v[4] = 0x53bb8085u; r2.v[5] = 0x8c49833du; r2.v[6] = 0x7f4e44a5u; r2.v[7] = 0x0216d0b1u;
+    // Montgomery products with one factor < q are valid for any 256-bit other factor (result < 2q, reduced once)
+    const Fr lo_red = fr_mul(fr_mul(lo, r2), raw1);  // lo*R*R^-1 = lo mod q
+    const Fr hi_red = fr_mul(hi, r2);                // hi*2^256 mod q
+    return fr_add(lo_red, hi_red);
+}
 
-    for (size_t x = (size_t)blockIdx.x * BLOCK + threadIdx.x; x < a.half; x += (size_t)gridDim.x * BLOCK) {
-        Fr e0, e1, s0, s1;
-        load_pair<FOLD>(a.src[0], a.dst[0], x, a.half, r, e0, e1);
-        load_pair<FOLD>(a.src[1], a.dst[1], x, a.half, r, s0, s1);
-        if (GATE == GATE_CIPHER) {
-            Fr r0, r1;
-            load_pair<FOLD>(a.src[2], a.dst[2], x, a.half, r, r0, r1);
-            s0 = fr_add(fr_add(r0, ark), s0);  // cipher.go:34-35  tmp = vR + Ark + vL
-            s1 = fr_add(fr_add(r1, ark), s1);
+template <int NEV, int BLOCK>
+__device__ __forceinline__ void grid_reduce_wide(uint32_t* sm, const ReduceOut& out) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    // block tree over threads, all NEV accumulators at every level
+#pragma unroll 1
+    for (int stride = BLOCK / 2; stride >= 1; stride >>= 1) {
+        const int items = NEV * stride;
+#pragma unroll 1
+        for (int it = tid; it < items; it += BLOCK) {
+            const int k = it / stride, i = it - k * stride;
+            wide_pair_add<BLOCK>(sm, k, i, stride);
         }
-        const Fr de = fr_sub(e1, e0), ds = fr_sub(s1, s0);
-        // t = 0 and t = 1 use the table values directly (algo.go:107-147); t >= 2 by repeated addition (:149-199)
-        acc[0] = fr_add(acc[0], fr_mul(e0, GATE == GATE_CIPHER ? fr_pow7(s0) : s0));
-        acc[1] = fr_add(acc[1], fr_mul(e1, GATE == GATE_CIPHER ? fr_pow7(s1) : s1));
-        Fr e = e1, s = s1;
+        __syncthreads();
+    }
+    __shared__ bool is_last_w;
+    Fr mine = fr_zero();
+    if (tid < NEV) {
+        uint32_t w[9];
 #pragma unroll
-        for (int t = 2; t < NEV; t++) {
-            e = fr_add(e, de);
-            s = fr_add(s, ds);
-            acc[t] = fr_add(acc[t], fr_mul(e, GATE == GATE_CIPHER ? fr_pow7(s) : s));
+        for (int l = 0; l < 9; l++) w[l] = sm[(tid * 9 + l) * BLOCK];
+        mine = fr_from_wide(w);
+    }
+    if (gridDim.x == 1) {
+        if (tid < NEV) fr_store(out.result + tid, mine);
+    } else {
+        if (tid < NEV) fr_store(out.partials + (size_t)blockIdx.x * NEV + tid, mine);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last_w = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (!is_last_w) return;
+        __threadfence();
+        // last block: modular sum of the per-block partials (reuses the shared buffer with the Fr layout)
+#pragma unroll 1
+        for (int k = 0; k < NEV; k++) {
+            Fr s = fr_zero();
+#pragma unroll 1
+            for (unsigned b = tid; b < gridDim.x; b += BLOCK) s = fr_add(s, fr_load(out.partials + (size_t)b * NEV + k));
+#pragma unroll
+            for (int l = 0; l < 8; l++) sm[(k * 8 + l) * BLOCK + tid] = s.v[l];
+        }
+        smem_tree_reduce<NEV, BLOCK>(sm, tid);
+        if (tid < NEV) fr_store(out.result + tid, smem_get<BLOCK>(sm, tid, 0));
+        if (tid == 0) *out.ticket = 0;
+    }
+    if (out.flag) {
+        if (tid < NEV) __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            *out.flag = out.seq;
         }
     }
-    grid_reduce<NEV, BLOCK>(acc, a.red, sm);
+}
+
+template <int GATE, bool FOLD, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_round(const RoundArgs a) {
+    constexpr int NEV = GateTraits<GATE>::NEV;
+    extern __shared__ uint32_t sm[];  // NEV * 9 * BLOCK words
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int i = tid; i < NEV * 9 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
+    const Fr r = fr_unpack(a.r);
+
+    for (size_t x = (size_t)blockIdx.x * BLOCK + tid; x < a.half; x += (size_t)gridDim.x * BLOCK) {
+        Fr e, de, s, ds;
+        {
+            Fr e1;
+            load_pair<FOLD>(a.src[0], a.dst[0], x, a.half, r, e, e1);
+            de = fr_sub(e1, e);
+        }
+        if (GATE == GATE_CIPHER) {
+            // s_t = X0_t + X1_t + ark  (cipher.go:34-35): sum bottom and top values over the two input tables
+            Fr s1 = fr_unpack(a.ark);
+            s = s1;
+#pragma unroll 1
+            for (int tb = 1; tb <= 2; tb++) {
+                Fr b, t;
+                load_pair<FOLD>(a.src[tb], a.dst[tb], x, a.half, r, b, t);
+                s = fr_add(s, b);
+                s1 = fr_add(s1, t);
+            }
+            ds = fr_sub(s1, s);
+        } else {
+            Fr s1;
+            load_pair<FOLD>(a.src[1], a.dst[1], x, a.half, r, s, s1);
+            ds = fr_sub(s1, s);
+        }
+        // evals[t] += eq_t * gate(s_t), t = 0..NEV-1; (e,s) advance by the differences (algo.go:149-199)
+#pragma unroll 1
+        for (int t = 0; t < NEV; t++) {
+            const Fr term = fr_mul(e, GATE == GATE_CIPHER ? fr_pow7(s) : s);
+            wide_acc_add<BLOCK>(sm + (size_t)t * 9 * BLOCK + tid, term);
+            e = fr_add(e, de);
+            s = fr_add(s, ds);
+        }
+    }
+    grid_reduce_wide<NEV, BLOCK>(sm, a.red);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -335,7 +463,8 @@ __global__ void __launch_bounds__(256) k_bench_imad_wide(uint64_t* out, int iter
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
 }
 // kind 1: two independent dependent-chains of fr_mul per thread (what the prover kernels look like)
-__global__ void __launch_bounds__(256) k_bench_fr_mul(FrRaw* out, int iters, uint32_t seed) {
+__global__ void k_bench_fr_mul(FrRaw* out, int iters, uint32_t seed) {
+    extern __shared__ uint32_t sm_dummy[];  // only used to limit occupancy from the host side
     Fr a = fr_one(), b = fr_one();
     a.v[0] ^= seed + threadIdx.x;
     b.v[1] ^= seed + blockIdx.x;
@@ -348,6 +477,45 @@ __global__ void __launch_bounds__(256) k_bench_fr_mul(FrRaw* out, int iters, uin
         c = fr_mul(c, d);
     }
     fr_store(out + (size_t)blockIdx.x * blockDim.x + threadIdx.x, fr_add(a, c));
+}
+// kind 3: a single dependent chain per thread
+__global__ void k_bench_fr_mul1(FrRaw* out, int iters, uint32_t seed) {
+    extern __shared__ uint32_t sm_dummy[];
+    Fr a = fr_one(), b = fr_one();
+    a.v[0] ^= seed + threadIdx.x;
+    b.v[1] ^= seed + blockIdx.x;
+    a = fr_reduce_once(a);
+    b = fr_reduce_once(b);
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        a = fr_mul(a, b);
+        a = fr_mul(a, b);
+    }
+    fr_store(out + (size_t)blockIdx.x * blockDim.x + threadIdx.x, a);
+}
+// kind 2: carry-chained IMAD.WIDE.U32.X: four independent 4-column chains per step (16 wide MACs)
+__global__ void __launch_bounds__(256) k_bench_imad_wide_x(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t c[4][9];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int i = 0; i < 9; i++) c[k][i] = seed * (k + 1) + i + threadIdx.x;
+    const uint32_t x0 = seed ^ threadIdx.x, x1 = x0 * 3u, x2 = x0 * 5u, x3 = x0 * 7u, y = seed + blockIdx.x;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                chain4(c[k][0], c[k][1], c[k][2], c[k][3], c[k][4], c[k][5], c[k][6], c[k][7], c[k][8], x0, x1, x2, x3, y);
+        }
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int i = 0; i < 9; i++) r += c[k][i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 }  // namespace gkr

@@ -21,6 +21,8 @@ class Stats(ctypes.Structure):
         ("fr_mul_assign", ctypes.c_uint64),
         ("fr_mul_round", ctypes.c_uint64),
         ("bytes_round", ctypes.c_uint64),
+        ("h2d_bytes", ctypes.c_uint64),
+        ("d2h_bytes", ctypes.c_uint64),
     ]
 
 

@@ -125,6 +125,8 @@ typedef struct {
     uint64_t fr_mul_assign;       /* algorithmic field multiplications issued to the device, per class   */
     uint64_t fr_mul_round;
     uint64_t bytes_round;         /* algorithmic bytes moved by the round kernels                        */
+    uint64_t h2d_bytes;           /* bytes copied host->device / device->host by the library             */
+    uint64_t d2h_bytes;
 } gkrb200_stats;
 int gkrb200_stats_reset(gkrb200_ctx *ctx);
 int gkrb200_stats_get(gkrb200_ctx *ctx, gkrb200_stats *out);
