@@ -64,9 +64,14 @@ def get_challenge(seed):
     return mimc_hash(seed)
 
 
+def random_fr_element(i):
+    """common/common.go:52: SetUint64(uint64(i)*uint64(i) ^ 0xf45c9df123f) -- the product wraps at 2^64"""
+    return (((i * i) & 0xFFFFFFFFFFFFFFFF) ^ 0xF45C9DF123F) % Q
+
+
 def random_fr_array(n):
     """common/common.go:49-55"""
-    return [(((i * i) & 0xFFFFFFFFFFFFFFFF) ^ 0xF45C9DF123F) % Q for i in range(n)]
+    return [random_fr_element(i) for i in range(n)]
 
 
 # ------------------------------------------------------------------ poly/

@@ -1,0 +1,100 @@
+"""CPU tests of the C-ABI library: it loads, exports every symbol include/gkrb200.h declares, its host-side
+transcript pieces agree with the oracle, and device entry points fail loudly without a GPU (no CPU fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        return subprocess.run(["nvidia-smi", "-L"], capture_output=True, timeout=20).returncode == 0
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    import gkrb200
+    hdr = open(os.path.join(ROOT, "include", "gkrb200.h")).read()
+    names = sorted(set(re.findall(r"\b(gkrb200_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    L = gkrb200.lib()
+    for n in names:
+        assert hasattr(L, n), "symbol %s declared in include/gkrb200.h is not exported" % n
+    out = subprocess.run(["nm", "-D", "--defined-only", gkrb200._lib.SO_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (gkrb200_[a-z0-9_]+)", out))
+    assert set(names) <= exported
+    assert L.gkrb200_version().startswith(b"gkrb200")
+    assert L.gkrb200_proof_vec_len(10) == 10243  # 1006*bn+183 (prover/gadget/hints.go:76-116)
+
+
+def test_library_is_built_for_sm100a_only():
+    import gkrb200
+    out = subprocess.run(["cuobjdump", "--list-elf", gkrb200._lib.SO_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_no_cpu_fallback_without_a_device():
+    import gkrb200
+    if _has_gpu():
+        pytest.skip("a GPU is present")
+    with pytest.raises(gkrb200.GkrB200Error) as e:
+        gkrb200.Context(device=0, max_bn=4)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """the product path must never import/link oracle/ (it is test infrastructure)"""
+    pkg = os.path.join(ROOT, "gkr-mimc_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "coracle" not in txt and "pyref" not in txt and "liboracle" not in txt and "gkr_oracle" not in txt, os.path.join(dirpath, f)
+    out = subprocess.run(["ldd", os.path.join(pkg, "libgkrb200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def test_host_transcript_matches_oracle(oracle):
+    """common.GetChallenge / hash.MimcHash and poly.InterpolateOnRange run on the host inside the product"""
+    import gkrb200
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 3, 9, 91):
+        x = oracle.to_mont([int.from_bytes(rng.bytes(40), "little") % oracle.Q for _ in range(n)]).reshape(n, 4)
+        assert np.array_equal(gkrb200.common.GetChallenge(x), oracle.mimc_hash(x))
+    assert oracle.from_mont(gkrb200.common.GetChallenge(oracle.to_mont([12])))[0] == \
+        1808205620575546259657963589762746470347087906694759866517376279978241663265  # hash/hash_test.go:21-27
+    for n in range(1, 13):
+        v = oracle.random_fr_array(n + 5)[5:]
+        assert np.array_equal(gkrb200.poly.InterpolateOnRange(v), oracle.interpolate_on_range(v))
+
+
+def test_montgomery_conversions_and_random_array(oracle):
+    import gkrb200
+    vals = [0, 1, 5, oracle.Q - 1, 2**200 + 12345]
+    reg = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for j in range(4):
+            reg[i, j] = (v >> (64 * j)) & (2**64 - 1)
+    m = gkrb200.common.ToMontgomery(reg)
+    assert np.array_equal(m, oracle.to_mont(vals))
+    assert np.array_equal(gkrb200.common.FromMontgomery(m), reg)
+    assert np.array_equal(gkrb200.common.RandomFrArray(1000), oracle.random_fr_array(1000))
+    assert oracle.from_mont(gkrb200.common.SetUint64([0, 7, 2**64 - 1])) == [0, 7, 2**64 - 1]
+
+
+def test_argument_errors_before_any_device_work():
+    import gkrb200
+    L = gkrb200.lib()
+    out = np.zeros(4, dtype=np.uint64)
+    assert L.gkrb200_mimc_hash(None, 3, out.ctypes.data_as(ctypes.c_void_p)) == -1
+    assert b"null" in L.gkrb200_last_error()
+    assert L.gkrb200_interpolate(out.ctypes.data_as(ctypes.c_void_p), 13, out.ctypes.data_as(ctypes.c_void_p)) == -1
+    h = ctypes.c_void_p()
+    assert L.gkrb200_init(ctypes.byref(h), 0, 99, None) == -1
