@@ -248,6 +248,13 @@ __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
 }
 __device__ __forceinline__ Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
 
+// Out-of-line copy of the multiplier (register ABI, no stack: 16 words in, 8 out).  Kernels that issue many
+// multiplications per work item call this one ~3 KB body instead of inlining it 20-50 times: the round kernels
+// shrink from ~50 KB to a few KB of SASS, which keeps them inside the instruction cache (profiles/: the inlined
+// v1/v2 kernels showed no_instruction stalls and a 40 us floor for one-wave launches).
+__device__ __noinline__ Fr fr_mulc(const Fr a, const Fr b) { return fr_mul(a, b); }
+__device__ __forceinline__ Fr fr_sqrc(const Fr& a) { return fr_mulc(a, a); }
+
 // x^7 = ((x^2 * x)^2) * x  -- same chain as hash/poseidon.go:129-135 and circuit/gates/cipher.go:37-40
 __device__ __forceinline__ Fr fr_pow7(const Fr& x) {
     Fr t = fr_sqr(x);

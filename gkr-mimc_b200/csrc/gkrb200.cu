@@ -111,12 +111,13 @@ struct gkrb200_ctx {
     FrRaw* d_mults = nullptr;    // [MAX_CLAIMS]
     FrRaw* partials = nullptr;   // [max_grid][MAX_EV]
     unsigned int* ticket = nullptr;
-    FrRaw* d_local = nullptr;    // [16] this rank's contribution (multi-GPU)
+    FrRaw* d_local = nullptr;    // [32] this rank's contribution (multi-GPU); [16..19) residual entries of the last fold
     FrRaw* d_all = nullptr;      // [8*16]
+    uint32_t* partials_w = nullptr;  // [max_grid][8][9] per-block 288-bit sums of the factored cipher round
     int max_grid = 0;
 
     // pinned, device-mapped result slot
-    FrRaw* h_result = nullptr;  // [16]
+    FrRaw* h_result = nullptr;  // [128] (4 KiB: 8 ranks x 8 wide sums x 36 B fit)
     volatile uint32_t* h_flag = nullptr;
     uint32_t seq = 0;
     H::Fr* h_stage = nullptr;  // pinned staging for qprimes/mults uploads [MAX_CLAIMS*(max_bn+1)]
@@ -156,8 +157,14 @@ struct gkrb200_ctx {
 
     int build_eq(const H::Fr* qprimes, size_t n_q, int bn_local, const H::Fr* mults, FrRaw* out);
     int sumcheck(const FrRaw* x0, const FrRaw* x1, int bn_total, const H::Fr* qprimes, size_t n_q, const H::Fr* claims, size_t n_claims,
-                 int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out);
+                 int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out,
+                 const H::Fr* trusted_claim = nullptr);
+    size_t par8_max_pairs = 8192;  // rounds with at most this many pairs spread one pair over 8 lanes
+    bool force_generic = false;  // test hook: run cipher layers through the generic evaluate-at-9-points kernel
     int exchange_and_fetch(int nacc, H::Fr* out);
+    int exchange_and_fetch_wide(int nm, H::Fr* out);
+    int sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn_total, const H::Fr* q, const H::Fr* trusted_claim, const H::Fr& ark, bool use_shards,
+                    H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out);
 };
 
 // ------------------------------------------------------------------------------------------------ profiling helpers
@@ -237,6 +244,52 @@ static inline int grid_for(size_t work_items, int block, int max_grid) {
     return (int)g;
 }
 
+
+// ------------------------------------------------------------------------------------------------ factored cipher round: launch plumbing
+static constexpr int CF_BLOCK = 128;
+static constexpr int CF_MINB = 4;
+
+typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
+static cf_kernel_t cf_kernel(bool fold, int nm, bool par8) {
+    using namespace gkr;
+#define CF_K(F, N, P) k_round_cf<F, N, P, CF_BLOCK, CF_MINB>
+    static const cf_kernel_t tab[2][2][2] = {{{CF_K(false, 7, 1), CF_K(false, 7, 8)}, {CF_K(false, 8, 1), CF_K(false, 8, 8)}},
+                                             {{CF_K(true, 7, 1), CF_K(true, 7, 8)}, {CF_K(true, 8, 1), CF_K(true, 8, 8)}}};
+#undef CF_K
+    return tab[fold ? 1 : 0][nm == 8 ? 1 : 0][par8 ? 1 : 0];
+}
+static int set_cf_attrs() {
+    for (int f = 0; f < 2; f++)
+        for (int n = 7; n <= 8; n++)
+            for (int p = 0; p < 2; p++)
+                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, p), cudaFuncAttributeMaxDynamicSharedMemorySize, n * 9 * CF_BLOCK * 4));
+    return 0;
+}
+
+// 288-bit plain sums (one per rank) -> canonical field element
+static H::Fr wide_to_fr(const uint32_t* w, int n_ranks, size_t rank_stride_words) {
+    uint64_t acc[10] = {0};
+    for (int g = 0; g < n_ranks; g++)
+        for (int l = 0; l < 9; l++) acc[l] += w[(size_t)g * rank_stride_words + l];
+    for (int l = 0; l < 9; l++) {  // carry-normalise to 32-bit limbs
+        acc[l + 1] += acc[l] >> 32;
+        acc[l] &= 0xffffffffu;
+    }
+    H::Fr lo{{acc[0] | (acc[1] << 32), acc[2] | (acc[3] << 32), acc[4] | (acc[5] << 32), acc[6] | (acc[7] << 32)}};
+    const uint64_t hi = acc[8] | (acc[9] << 32);  // < 2^36
+    for (;;) {  // lo < 2^256 < 6q
+        H::ull s0, s1, s2, s3;
+        unsigned char b = _subborrow_u64(0, lo.l[0], H::Q[0], &s0);
+        b = _subborrow_u64(b, lo.l[1], H::Q[1], &s1);
+        b = _subborrow_u64(b, lo.l[2], H::Q[2], &s2);
+        b = _subborrow_u64(b, lo.l[3], H::Q[3], &s3);
+        if (b) break;
+        lo = H::Fr{{s0, s1, s2, s3}};
+    }
+    // hi * 2^256 mod q = mont(hi, R^2)
+    return H::add(lo, H::mul(H::Fr{{hi, 0, 0, 0}}, H::Fr{{H::R2[0], H::R2[1], H::R2[2], H::R2[3]}}));
+}
+
 // ------------------------------------------------------------------------------------------------ init / free
 extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* stream) {
     if (!out || max_bn < 0 || max_bn > 26) return fail(GKRB200_ERR_ARG, "bad arguments to gkrb200_init (max_bn=%d)", max_bn);
@@ -268,7 +321,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     const int nsmall = (max_bn + 1) / 2;
     const size_t small = (size_t)1 << nsmall;
     size_t total = 93 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
-                   (size_t)c->max_grid * MAX_EV + 16 + 8 * 16 + 64;
+                   (size_t)c->max_grid * MAX_EV + 32 + 8 * 16 + 64 + ((size_t)c->max_grid * 8 * 9 * 4 + 31) / 32;
     cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
     if (me != cudaSuccess) {
         delete c;
@@ -283,12 +336,13 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     c->d_q = p; p += (size_t)MAX_CLAIMS * (max_bn + 1);
     c->d_mults = p; p += MAX_CLAIMS;
     c->partials = p; p += (size_t)c->max_grid * MAX_EV;
-    c->d_local = p; p += 16;
+    c->d_local = p; p += 32;
     c->d_all = p; p += 8 * 16;
+    c->partials_w = (uint32_t*)p; p += ((size_t)c->max_grid * 8 * 9 * 4 + 31) / 32;
     CUDA_TRY(cudaMalloc(&c->ticket, 64));
     CUDA_TRY(cudaMemset(c->ticket, 0, 64));
-    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 16 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
-    c->h_flag = (volatile uint32_t*)(c->h_result + 16);
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 128 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
+    c->h_flag = (volatile uint32_t*)(c->h_result + 128);
     *c->h_flag = 0;
     CUDA_TRY(cudaHostAlloc((void**)&c->h_stage, (size_t)MAX_CLAIMS * (max_bn + 2) * sizeof(H::Fr), cudaHostAllocDefault));
     // opt in to the dynamic shared memory the round kernels need
@@ -297,6 +351,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
+    TRY(set_cf_attrs());
     *out = c;
     return 0;
 }
@@ -496,10 +551,13 @@ static void host_fold(H::Fr* t, size_t len, const H::Fr& r) {
 // x0/x1: device tables of this rank (n_local = 2^(bn_total - log_world) entries when use_shards), never modified.
 // qprimes: n_q * bn_total.  Returns bn_total*(nev) coefficients, bn_total challenges, 1+arity final claims.
 int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr* qprimes, size_t n_q, const H::Fr* claims, size_t n_claims,
-                          int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out) {
+                          int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out,
+                          const H::Fr* trusted_claim) {
     // sumcheck/prover.go:113-115
     if (n_claims != n_q && n_q > 1)
         return fail(GKRB200_ERR_ARG, "provided a multi-instance %zu but the number of claims does not match %zu", n_q, n_claims);
+    if (gate == gkr::GATE_CIPHER && n_q == 1 && !force_generic)
+        return sumcheck_cf(x0, x1, bn, qprimes, trusted_claim, ark, use_shards, proof_out, challenges_out, final_out);
     const int W = use_shards ? world : 1, LW = use_shards ? log_world : 0;
     const int bnl = bn - LW;  // rounds run on the device
     const int nev = gate == gkr::GATE_CIPHER ? 9 : 3;
@@ -606,12 +664,12 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         f.n_tables = 1 + nin;
         for (int i = 0; i < 1 + nin; i++) {
             f.src[i] = cur[i];
-            f.dst[i] = d_local + 8 + i;
+            f.dst[i] = d_local + 16 + i;
         }
         f.half = 1;
         memcpy(&f.r, &r, 32);
         LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 32, 0, f);
-        CUDA_TRY(cudaMemcpyAsync(h_stage, d_local + 8, (1 + nin) * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(h_stage, d_local + 16, (1 + nin) * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         memcpy(resid, h_stage, (1 + nin) * sizeof(H::Fr));
         st.d2h_bytes += (1 + nin) * sizeof(H::Fr);
@@ -663,6 +721,219 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
     return 0;
 }
 
+
+// Wide variant for the factored cipher round: nm 288-bit sums per rank.
+int gkrb200_ctx::exchange_and_fetch_wide(int nm, H::Fr* out) {
+    const int W = eff_world();
+    const size_t words = (size_t)nm * 9;
+    if (W > 1) {
+        const double t0 = now_ms();
+        NCCL_TRY(g_nccl.AllGather(d_local, d_all, words * 4, ncclUint8, comm, stream));
+        st.launches_total++;
+        st.launches[KC_MISC]++;
+        gkr::k_publish_words<<<1, 128, 0, stream>>>((const uint32_t*)d_all, (int)(words * W), (uint32_t*)h_result, h_flag, seq);
+        st.comm_ms += now_ms() - t0;
+    }
+    TRY(wait_flag(seq));
+    const uint32_t* w = (const uint32_t*)h_result;
+    for (int i = 0; i < nm; i++) out[i] = wide_to_fr(w + (size_t)i * 9, W, words);
+    st.d2h_bytes += words * 4 * (size_t)W + 4;
+    return 0;
+}
+
+// montgomery-form small integers
+static const H::Fr& binom7(int i) {
+    static const H::Fr t[8] = {H::from_u64(1), H::from_u64(7), H::from_u64(21), H::from_u64(35), H::from_u64(35), H::from_u64(21), H::from_u64(7), H::from_u64(1)};
+    return t[i];
+}
+// out[i] = 1/v[i] (Montgomery batch inversion: one field inversion per layer); ok[i] = false where v[i] == 0
+static void batch_inverse(const H::Fr* v, int n, H::Fr* out, bool* ok) {
+    H::Fr pre[32], acc = H::one();
+    for (int i = 0; i < n; i++) {
+        pre[i] = acc;
+        ok[i] = !H::is_zero(v[i]);
+        if (ok[i]) acc = H::mul(acc, v[i]);
+    }
+    H::Fr ia = H::inv(acc);
+    for (int i = n - 1; i >= 0; i--) {
+        if (!ok[i]) {
+            out[i] = H::zero();
+            continue;
+        }
+        out[i] = H::mul(ia, pre[i]);
+        ia = H::mul(ia, v[i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ sumcheck.Prove, cipher gate, one claim
+// Same outputs as Ctx::sumcheck (sumcheck/prover.go:46-90) for gate = CipherGate and a single qPrime, through the factored
+// round described above k_round_cf in kernels.cuh.  trusted_claim: the value of sum_x eq(q,x)*gate(X0,X1)(x) when the caller
+// KNOWS it (gkr.Prove: Claims[layer][0], produced by this prover for a consistent assignment) or nullptr; with it round 0
+// also skips the 8th coefficient sum.  Rounds k >= 1 always carry their own running claim S_{k-1}(r_{k-1}).
+int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr* q, const H::Fr* trusted_claim, const H::Fr& ark, bool use_shards,
+                             H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out) {
+    const int W = use_shards ? world : 1, LW = use_shards ? log_world : 0;
+    const int bnl = bn - LW;
+    if (bnl > 26) return fail(GKRB200_ERR_ARG, "too many variables (%d)", bnl);
+    const H::Fr one = H::one();
+    // this rank's slice of eq(q,.) carries the factor of its fixed low address bits
+    H::Fr seed_all[8];
+    for (int g = 0; g < W; g++) {
+        H::Fr sd = one;
+        for (int b = 0; b < LW; b++) {
+            const H::Fr& qb = q[bn - 1 - b];
+            sd = H::mul(sd, ((g >> b) & 1) ? qb : H::sub(one, qb));
+        }
+        seed_all[g] = sd;
+    }
+    const int c = bnl / 2;  // variables in the low suffix table
+    if (bnl > 0) {
+        gkr::EqSuffixArgs ea{};
+        memcpy(ea.q, q, (size_t)bnl * 32);
+        memcpy(&ea.seed, &seed_all[W > 1 ? rank : 0], 32);
+        ea.n = bnl;
+        ea.c = c;
+        ea.outB = lo;
+        ea.outA = hi;
+        LAUNCH(this, KC_EQ, gkr::k_eq_suffix, 2, 256, 0, ea);
+        CUDA_TRY(cudaGetLastError());
+    }
+    H::Fr qinv[32];
+    bool qinv_ok[32];
+    batch_inverse(q, bnl, qinv, qinv_ok);
+
+    const FrRaw* cur[2] = {x0, x1};
+    FrRaw* dstp[2] = {scratch[1], scratch[2]};
+    H::Fr ck = one, cl = trusted_claim ? *trusted_claim : H::zero(), r = H::zero();
+    bool have_cl = trusted_claim != nullptr;
+    H::Fr m[8], sc[8];
+    for (int k = 0; k < bnl; k++) {
+        const int mk = bnl - 1 - k;  // variables of x'
+        const size_t half = (size_t)1 << mk;
+        const bool do_fold = k > 0;
+        const int nm = (have_cl && qinv_ok[k]) ? 7 : 8;
+        const bool par8 = half <= par8_max_pairs;
+        gkr::RoundCfArgs a{};
+        for (int i = 0; i < 2; i++) {
+            a.src[i] = cur[i];
+            a.dst[i] = dstp[i];
+        }
+        a.half = half;
+        memcpy(&a.r, &r, 32);
+        memcpy(&a.ark, &ark, 32);
+        if (mk > c) {
+            a.tA = hi + ((size_t)1 << (mk - c));
+            a.tB = lo + ((size_t)1 << c);
+        } else {
+            a.tA = nullptr;
+            a.tB = lo + ((size_t)1 << mk);
+        }
+        a.c = c;
+        ++seq;
+        a.red.partials = partials_w;
+        a.red.ticket = ticket;
+        a.red.result = W > 1 ? (uint32_t*)d_local : (uint32_t*)h_result;
+        a.red.flag = W > 1 ? nullptr : h_flag;
+        a.red.seq = seq;
+        const int grid = grid_for(par8 ? half * 8 : half, CF_BLOCK, max_grid);
+        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, CF_BLOCK, (size_t)nm * 9 * CF_BLOCK * 4, a);
+        CUDA_TRY(cudaGetLastError());
+        st.fr_mul_round += (uint64_t)half * ((nm == 8 ? 20 : 18) + (mk > c ? 1 : 0) + (do_fold ? 4 : 0));
+        st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
+        if (do_fold) {
+            cur[0] = dstp[0];
+            cur[1] = dstp[1];
+        }
+        TRY(exchange_and_fetch_wide(nm, m));
+        const double t0 = now_ms();
+        const H::Fr w0 = H::sub(one, q[k]), w1 = H::sub(q[k], w0);  // eq(q_k, t) = w0 + w1*t
+        if (nm == 7) {
+            // p(0) + p(1) = claim  =>  S(1) = (cl - w0*S(0)) / q_k ;  m_7 = S(1) - sum_{i<7} C(7,i) m_i
+            H::Fr acc = H::mul(H::sub(cl, H::mul(w0, m[0])), qinv[k]);
+            for (int i = 0; i < 7; i++) {
+                sc[i] = i == 0 ? m[0] : H::mul(binom7(i), m[i]);
+                acc = H::sub(acc, sc[i]);
+            }
+            sc[7] = acc;
+        } else {
+            for (int i = 0; i < 8; i++) sc[i] = (i == 0 || i == 7) ? m[i] : H::mul(binom7(i), m[i]);
+        }
+        // p(t) = ck * (w0 + w1 t) * S(t), coefficients low -> high (what InterpolateOnRange yields, poly/lagrange.go:96)
+        const H::Fr cw0 = H::mul(ck, w0), cw1 = H::mul(ck, w1);
+        H::Fr* coeffs = proof_out + (size_t)k * 9;
+        coeffs[0] = H::mul(cw0, sc[0]);
+        for (int j = 1; j < 8; j++) coeffs[j] = H::add(H::mul(cw0, sc[j]), H::mul(cw1, sc[j - 1]));
+        coeffs[8] = H::mul(cw1, sc[7]);
+        r = H::mimc_hash(coeffs, 9);  // common/challenge.go:10
+        challenges_out[k] = r;
+        cl = H::eval_univariate(sc, 8, r);  // next round's claim / c_{k+1}
+        have_cl = true;
+        ck = H::mul(ck, H::add(w0, H::mul(w1, r)));
+        st.transcript_ms += now_ms() - t0;
+        st.rounds++;
+    }
+    // ---- last fold on the device: tables of length 2 -> this rank's residual entries of X0, X1
+    H::Fr resid[3];
+    resid[0] = H::mul(ck, seed_all[W > 1 ? rank : 0]);
+    if (bnl > 0) {
+        gkr::FoldArgs f{};
+        f.n_tables = 2;
+        for (int i = 0; i < 2; i++) {
+            f.src[i] = cur[i];
+            f.dst[i] = d_local + 16 + i;
+        }
+        f.half = 1;
+        memcpy(&f.r, &r, 32);
+        LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 32, 0, f);
+        CUDA_TRY(cudaMemcpyAsync(h_stage, d_local + 16, 2 * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(h_stage, x0, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(h_stage + 1, x1, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    memcpy(resid + 1, h_stage, 2 * sizeof(H::Fr));
+    st.d2h_bytes += 2 * sizeof(H::Fr);
+    if (W == 1) {
+        for (int i = 0; i < 3; i++) final_out[i] = resid[i];
+        return 0;
+    }
+    // ---- sharded: gather the residual X entries (entry g = rank g's value); the eq residuals are closed-form
+    {
+        const double t0 = now_ms();
+        memcpy(h_stage, resid + 1, 2 * sizeof(H::Fr));
+        TRY(upload(d_local, h_stage, 2));
+        NCCL_TRY(g_nccl.AllGather(d_local, d_all, 2 * sizeof(FrRaw), ncclUint8, comm, stream));
+        CUDA_TRY(cudaMemcpyAsync(h_stage + 4, d_all, (size_t)W * 2 * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        st.comm_ms += now_ms() - t0;
+    }
+    H::Fr te[8], t0v[8], t1v[8], evals[MAX_EV];
+    for (int g = 0; g < W; g++) {
+        te[g] = H::mul(ck, seed_all[g]);
+        t0v[g] = h_stage[4 + 2 * g];
+        t1v[g] = h_stage[4 + 2 * g + 1];
+    }
+    size_t rl = (size_t)W;
+    for (int k = bnl; k < bn; k++) {
+        const double t0 = now_ms();
+        host_round_eval(te, t0v, t1v, rl, gkr::GATE_CIPHER, ark, evals);
+        H::Fr* coeffs = proof_out + (size_t)k * 9;
+        lagrange.interpolate(evals, 9, coeffs);
+        r = H::mimc_hash(coeffs, 9);
+        challenges_out[k] = r;
+        host_fold(te, rl, r);
+        host_fold(t0v, rl, r);
+        host_fold(t1v, rl, r);
+        rl /= 2;
+        st.transcript_ms += now_ms() - t0;
+        st.rounds++;
+    }
+    final_out[0] = te[0];
+    final_out[1] = t0v[0];
+    final_out[2] = t1v[0];
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ circuit description
 // examples/mimc.go:10-37: layer 2 = Identity(0); layer i+3 = Cipher(Arks[i])(2, i == 0 ? 1 : i+2)
 static int layer_in(int layer, int in[2]) {
@@ -706,8 +977,10 @@ extern "C" int gkrb200_gkr_prove_mimc(gkrb200_ctx* c, const uint64_t* qprime, in
         const size_t n_q = layer == N_LAYERS - 1 ? 1 : (size_t)n_out(layer);
         const size_t n_cl = layer == N_LAYERS - 1 ? 0 : (size_t)n_out(layer);  // Claims[93] is nil (prover.go:27)
         H::Fr fin[3];
+        // Claims[layer][0] was produced by this prover from the assignment it computed itself: it IS sum eq*gate of this layer
+        const H::Fr* trusted = (gate == gkr::GATE_CIPHER && n_cl == 1) ? claims[layer].data() : nullptr;
         TRY(c->sumcheck(c->slot(in[0]), k > 1 ? c->slot(in[1]) : nullptr, bn, qps[layer].data(), n_q, claims[layer].data(), n_cl, gate, ark,
-                        c->sharded, sc[layer].data(), challenges.data(), fin));
+                        c->sharded, sc[layer].data(), challenges.data(), fin, trusted));
         for (int i = 0; i < k; i++) {  // prover.go:66-90
             const int at = pos_in_out(in[i], layer);
             claims[in[i]][(size_t)at] = fin[1 + i];
@@ -897,6 +1170,18 @@ extern "C" int gkrb200_set_profiling(gkrb200_ctx* c, int on) {
     c->ev_flush();
     c->profiling = on != 0;
     return 0;
+}
+
+extern "C" int gkrb200_set_option(gkrb200_ctx* c, int option, long value) {
+    if (!c) return fail(GKRB200_ERR_ARG, "null context");
+    switch (option) {
+        case GKRB200_OPT_GENERIC_CIPHER: c->force_generic = value != 0; return 0;
+        case GKRB200_OPT_PAR8_MAX_PAIRS:
+            if (value < 0) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
+            c->par8_max_pairs = (size_t)value;
+            return 0;
+        default: return fail(GKRB200_ERR_ARG, "unknown option %d", option);
+    }
 }
 
 extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, double* rate_out, double* ms_out) {

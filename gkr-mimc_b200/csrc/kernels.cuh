@@ -394,6 +394,266 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round(const RoundArgs a) {
     grid_reduce_wide<NEV, BLOCK>(sm, a.red);
 }
 
+// ================================================================================================
+// Factored cipher round (K3+K4, single-claim layers: 91 of the 92 sumchecks of the MiMC circuit).
+//
+// For one claim the eq table is a product, eq(q,x) = prod_j eq(q_j,x_j), so in round k (variables 0..k-1
+// already bound to r_0..r_{k-1}, MSB first as in poly/multilin.go:26-36) the folded table of
+// sumcheck/prover.go is   Eq_k[x_k, x'] = c_k * eq(q_k, x_k) * T_k[x'],   c_k = prod_{j<k} eq(q_j, r_j),
+// T_k = eq(q[k+1:], .).  The round polynomial of sumcheck/algo.go:54-205 therefore factors as
+//      p_k(t) = c_k * ((1-q_k)(1-t) + q_k t) * S_k(t),     S_k(t) = sum_x' T_k[x'] * (a(x') + t*b(x'))^7,
+// with a = X0[x'] + X1[x'] + ark (bottom half) and b = (top half) - a.  The device only produces the
+// coefficient sums  m_i = sum_x' T_k[x'] * a^(7-i) * b^i  (S_k(t) = sum_i C(7,i) m_i t^i): 18 field
+// multiplications per pair instead of the 45 of the evaluate-at-9-points form, no eq table in HBM, no eq
+// fold.  m_7 follows on the host from the running claim (p_k(0)+p_k(1) = claim); NM = 8 computes it on the
+// device for the rounds where no claim is available.  The host turns m into the very coefficients the
+// reference sends (exact field arithmetic: identical canonical values), see Ctx::sumcheck.
+//
+// T_k[x'] = A[x' >> c] * B[x' & (2^c-1)]  from two small suffix tables built per layer by k_eq_suffix
+// (or T_k = B[x'] once x' has <= c bits).  PAR = 8 spreads one pair over 8 lanes (lane j forms term j
+// with a uniform select-and-multiply ladder) so that small rounds are not bound by one thread's chain
+// of ~23 dependent multiplications.
+// ================================================================================================
+struct WideOut {
+    uint32_t* partials;       // [gridDim.x][NM][9] device scratch
+    unsigned int* ticket;     // device counter, zero between launches
+    uint32_t* result;         // NM x 9 words (288-bit plain sums, NOT reduced); device or mapped host memory
+    volatile uint32_t* flag;  // optional: set to seq once result is visible system-wide
+    uint32_t seq;
+};
+
+// Block tree over the per-thread 288-bit accumulators, then (grid > 1) a last-block pass over the per-block
+// sums.  No field multiplication anywhere: the host reduces the NM wide sums modulo q.
+template <int NM, int BLOCK>
+__device__ __forceinline__ void grid_reduce_wide_raw(uint32_t* sm, const WideOut& out) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+#pragma unroll 1
+    for (int stride = BLOCK / 2; stride >= 1; stride >>= 1) {
+        const int items = NM * stride;
+#pragma unroll 1
+        for (int it = tid; it < items; it += BLOCK) {
+            const int k = it / stride, i = it - k * stride;
+            wide_pair_add<BLOCK>(sm, k, i, stride);
+        }
+        __syncthreads();
+    }
+    __shared__ bool is_last_r;
+    if (gridDim.x == 1) {
+        if (tid < NM * 9) out.result[tid] = sm[tid * BLOCK];
+    } else {
+        if (tid < NM * 9) out.partials[(size_t)blockIdx.x * (NM * 9) + tid] = sm[tid * BLOCK];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last_r = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
+        __syncthreads();
+        if (!is_last_r) return;
+        __threadfence();
+        // last block: thread t sums the partials of blocks t, t+BLOCK, ... for every accumulator, then the tree again
+#pragma unroll 1
+        for (int k = 0; k < NM; k++) {
+            uint32_t a[9];
+#pragma unroll
+            for (int l = 0; l < 9; l++) a[l] = 0;
+#pragma unroll 1
+            for (unsigned b = tid; b < gridDim.x; b += BLOCK) {
+                const uint32_t* pp = out.partials + (size_t)b * (NM * 9) + k * 9;
+                uint32_t w[9];
+#pragma unroll
+                for (int l = 0; l < 9; l++) w[l] = __ldcg(pp + l);
+                asm("add.cc.u32 %0, %0, %9;\n\t"
+                    "addc.cc.u32 %1, %1, %10;\n\t"
+                    "addc.cc.u32 %2, %2, %11;\n\t"
+                    "addc.cc.u32 %3, %3, %12;\n\t"
+                    "addc.cc.u32 %4, %4, %13;\n\t"
+                    "addc.cc.u32 %5, %5, %14;\n\t"
+                    "addc.cc.u32 %6, %6, %15;\n\t"
+                    "addc.cc.u32 %7, %7, %16;\n\t"
+                    "addc.u32 %8, %8, %17;"
+                    : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8])
+                    : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]));
+            }
+#pragma unroll
+            for (int l = 0; l < 9; l++) sm[(k * 9 + l) * BLOCK + tid] = a[l];
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int stride = BLOCK / 2; stride >= 1; stride >>= 1) {
+            const int items = NM * stride;
+#pragma unroll 1
+            for (int it = tid; it < items; it += BLOCK) {
+                const int k = it / stride, i = it - k * stride;
+                wide_pair_add<BLOCK>(sm, k, i, stride);
+            }
+            __syncthreads();
+        }
+        if (tid < NM * 9) out.result[tid] = sm[tid * BLOCK];
+        if (tid == 0) *out.ticket = 0;
+    }
+    if (out.flag) {
+        if (tid < NM * 9) __threadfence_system();  // publish this thread's result word before the barrier
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            *out.flag = out.seq;
+        }
+    }
+}
+
+// Suffix eq tables of one layer's challenge vector q[0..n): block 0 builds the stages of the low part
+// v = q[n-c : n] (seeded with `seed`, the multi-GPU shard factor), block 1 those of the high part v = q[1 : n-c].
+// Stage j (j = 0..nv) = eq(last j variables of v, .) with 2^j entries at out[2^j .. 2^(j+1)), built by doubling
+// from the LAST variable (same recurrence as poly/eq.go:49-56, applied back to front so that every stage is kept).
+struct EqSuffixArgs {
+    FrRaw q[28];
+    FrRaw seed;
+    int n, c;
+    FrRaw* outB;  // 2^(c+1) entries
+    FrRaw* outA;  // 2^(n-c) entries
+};
+__global__ void __launch_bounds__(256) k_eq_suffix(const EqSuffixArgs a) {
+    const bool isA = blockIdx.x == 1;
+    const int nv = isA ? a.n - a.c - 1 : a.c;
+    const FrRaw* v = isA ? a.q + 1 : a.q + (a.n - a.c);
+    FrRaw* out = isA ? a.outA : a.outB;
+    if (threadIdx.x == 0) fr_store(out + 1, isA ? fr_one() : fr_unpack(a.seed));
+    __syncthreads();
+    for (int j = 0; j < nv; j++) {
+        const Fr var = fr_unpack(v[nv - 1 - j]);
+        const size_t cnt = (size_t)1 << j;
+        for (size_t y = threadIdx.x; y < cnt; y += blockDim.x) {
+            const Fr base = fr_load(out + cnt + y);
+            const Fr hi = fr_mulc(var, base);
+            fr_store(out + 2 * cnt + cnt + y, hi);
+            fr_store(out + 2 * cnt + y, fr_sub(base, hi));
+        }
+        __syncthreads();
+    }
+}
+
+struct RoundCfArgs {
+    const FrRaw* src[2];  // X0, X1 (FOLD: length 4*half, else 2*half)
+    FrRaw* dst[2];        // FOLD: folded tables, length 2*half
+    size_t half;          // number of pairs x'
+    FrRaw r;              // previous challenge (FOLD)
+    FrRaw ark;            // CipherGate.Ark
+    const FrRaw* tA;      // high suffix table of this round or nullptr
+    const FrRaw* tB;      // low table (2^c entries when tA != nullptr, else `half` entries)
+    int c;
+    WideOut red;
+};
+
+template <bool FOLD>
+__device__ __forceinline__ Fr load_fold_one(const FrRaw* src, FrRaw* dst, size_t idx, size_t stride2, const Fr& r) {
+    if (FOLD) {
+        const Fr lo = fr_load_stream(src + idx), hi = fr_load_stream(src + idx + stride2);
+        const Fr f = fr_add(lo, fr_mulc(r, fr_sub(hi, lo)));
+        fr_store(dst + idx, f);
+        return f;
+    }
+    return fr_load_stream(src + idx);
+}
+
+template <bool FOLD, int NM, int PAR, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
+    static_assert(NM == 7 || NM == 8, "7 coefficient sums (m_7 from the claim) or all 8");
+    static_assert(PAR == 1 || PAR == 8, "one thread or eight lanes per pair");
+    extern __shared__ uint32_t sm[];  // NM * 9 * BLOCK words
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int i = tid; i < NM * 9 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
+    const Fr r = fr_unpack(a.r);
+    const Fr ark = fr_unpack(a.ark);
+    const size_t half = a.half, m2 = 2 * half;
+    const size_t cmask = ((size_t)1 << a.c) - 1;
+
+    if (PAR == 1) {
+        for (size_t x = (size_t)blockIdx.x * BLOCK + tid; x < half; x += (size_t)gridDim.x * BLOCK) {
+            Fr av, bv;
+            {
+                const Fr b0 = load_fold_one<FOLD>(a.src[0], a.dst[0], x, m2, r);
+                const Fr t0 = load_fold_one<FOLD>(a.src[0], a.dst[0], x + half, m2, r);
+                const Fr b1 = load_fold_one<FOLD>(a.src[1], a.dst[1], x, m2, r);
+                const Fr t1 = load_fold_one<FOLD>(a.src[1], a.dst[1], x + half, m2, r);
+                av = fr_add(fr_add(b0, b1), ark);                 // cipher.go:34-35 on the bottom half
+                bv = fr_add(fr_sub(t0, b0), fr_sub(t1, b1));      // (top + ark) - (bottom + ark)
+            }
+            Fr u = a.tA ? fr_mulc(fr_load(a.tA + (x >> a.c)), fr_load(a.tB + (x & cmask))) : fr_load(a.tB + x);
+            Fr bp[NM];  // bp[i] = b^i, i >= 1
+            bp[1] = bv;
+            bp[2] = fr_sqrc(bv);
+            bp[3] = fr_mulc(bp[2], bv);
+            bp[4] = fr_sqrc(bp[2]);
+            bp[5] = fr_mulc(bp[4], bv);
+            bp[6] = fr_sqrc(bp[3]);
+            if (NM == 8) wide_acc_add<BLOCK>(sm + (size_t)7 * 9 * BLOCK + tid, fr_mulc(u, fr_mulc(bp[6], bv)));
+#pragma unroll
+            for (int i = 6; i >= 1; i--) {
+                u = fr_mulc(u, av);  // T * a^(7-i)
+                wide_acc_add<BLOCK>(sm + (size_t)i * 9 * BLOCK + tid, fr_mulc(u, bp[i]));
+            }
+            u = fr_mulc(u, av);
+            wide_acc_add<BLOCK>(sm + tid, u);
+        }
+    } else {
+        const int j = tid & 7;
+        const size_t pstride = (size_t)gridDim.x * (BLOCK / 8);
+        // block-uniform trip count (the shuffles below need every lane of the warp); surplus lanes redo pair 0 unrecorded
+        for (size_t xb = (size_t)blockIdx.x * (BLOCK / 8); xb < half; xb += pstride) {
+            const bool live = xb + (tid >> 3) < half;
+            const size_t x = live ? xb + (tid >> 3) : 0;
+            // lanes j and j+4 both form folded value (j & 3): 0 = X0 bottom, 1 = X0 top, 2 = X1 bottom, 3 = X1 top
+            const int tb = (j >> 1) & 1, top = j & 1;
+            const size_t idx = x + (top ? half : 0);
+            Fr f;
+            if (FOLD) {
+                const Fr lo = fr_load_stream(a.src[tb] + idx), hi = fr_load_stream(a.src[tb] + idx + m2);
+                f = fr_add(lo, fr_mulc(r, fr_sub(hi, lo)));
+                __syncwarp();  // in-place fold: all lanes have read their sources before any lane overwrites them
+                if (live && j < 4) fr_store(a.dst[tb] + idx, f);
+            } else {
+                f = fr_load_stream(a.src[tb] + idx);
+            }
+            Fr f0, f1, f2, f3;
+            const int base = (threadIdx.x & 31) & ~7;
+#pragma unroll
+            for (int l = 0; l < 8; l++) {
+                f0.v[l] = __shfl_sync(0xffffffffu, f.v[l], base + 0);
+                f1.v[l] = __shfl_sync(0xffffffffu, f.v[l], base + 1);
+                f2.v[l] = __shfl_sync(0xffffffffu, f.v[l], base + 2);
+                f3.v[l] = __shfl_sync(0xffffffffu, f.v[l], base + 3);
+            }
+            const Fr av = fr_add(fr_add(f0, f2), ark);
+            const Fr bv = fr_add(fr_sub(f1, f0), fr_sub(f3, f2));
+            Fr u = a.tA ? fr_mulc(fr_load(a.tA + (x >> a.c)), fr_load(a.tB + (x & cmask))) : fr_load(a.tB + x);
+            const Fr a2 = fr_sqrc(av), b2 = fr_sqrc(bv);
+            const Fr a4 = fr_sqrc(a2), b4 = fr_sqrc(b2);
+            // term j = T * a^(7-j) * b^j : bit i of j selects b^(2^i), otherwise a^(2^i)
+            Fr s1, s2, s4;
+#pragma unroll
+            for (int l = 0; l < 8; l++) {
+                s1.v[l] = (j & 1) ? bv.v[l] : av.v[l];
+                s2.v[l] = (j & 2) ? b2.v[l] : a2.v[l];
+                s4.v[l] = (j & 4) ? b4.v[l] : a4.v[l];
+            }
+            u = fr_mulc(fr_mulc(fr_mulc(u, s1), s2), s4);
+            if (live && j < NM) wide_acc_add<BLOCK>(sm + (size_t)j * 9 * BLOCK + tid, u);
+        }
+    }
+    grid_reduce_wide_raw<NM, BLOCK>(sm, a.red);
+}
+
+// copies nwords 32-bit words to (mapped) host memory and raises the flag (multi-GPU: after the all-gather)
+__global__ void k_publish_words(const uint32_t* __restrict__ src, int nwords, uint32_t* dst, volatile uint32_t* flag, uint32_t seq) {
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && flag) {
+        __threadfence_system();
+        *flag = seq;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Multi-GPU helpers
 // ------------------------------------------------------------------------------------------------

@@ -70,6 +70,7 @@ def lib():
     L.gkrb200_stats_reset.argtypes = [vp]
     L.gkrb200_stats_get.argtypes = [vp, ctypes.POINTER(Stats)]
     L.gkrb200_set_profiling.argtypes = [vp, i32]
+    L.gkrb200_set_option.argtypes = [vp, i32, ctypes.c_long]
     L.gkrb200_microbench.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = L
     return L

@@ -69,6 +69,11 @@ class Context:
     def set_profiling(self, on):
         check(lib().gkrb200_set_profiling(self._h, 1 if on else 0))
 
+    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS = 1, 2
+
+    def set_option(self, option, value):
+        check(lib().gkrb200_set_option(self._h, option, int(value)))
+
     def microbench(self, kind, iters):
         rate, ms = ctypes.c_double(), ctypes.c_double()
         check(lib().gkrb200_microbench(self._h, kind, iters, ctypes.byref(rate), ctypes.byref(ms)))

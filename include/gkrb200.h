@@ -133,6 +133,14 @@ int gkrb200_stats_get(gkrb200_ctx *ctx, gkrb200_stats *out);
 /* when on, every kernel launch is bracketed by CUDA events on the context's stream (adds ~us per launch) */
 int gkrb200_set_profiling(gkrb200_ctx *ctx, int on);
 
+/* Tunables / test hooks.  GKRB200_OPT_GENERIC_CIPHER (value 0/1): run single-claim cipher sumchecks through the
+ * generic evaluate-at-9-points kernel (the direct restatement of sumcheck/algo.go:54-205) instead of the factored
+ * coefficient-sum kernel; both must give identical bytes (tests/test_gpu_parity.py).
+ * GKRB200_OPT_PAR8_MAX_PAIRS: rounds with at most this many pairs spread one pair over 8 lanes.            */
+#define GKRB200_OPT_GENERIC_CIPHER 1
+#define GKRB200_OPT_PAR8_MAX_PAIRS 2
+int gkrb200_set_option(gkrb200_ctx *ctx, int option, long value);
+
 /* integer-pipe microbenchmarks for the roofline denominator: returns achieved rate.
  * kind 0: IMAD.WIDE.U32 issue rate (result in 1e9 wide-MACs/s); kind 1: dependent fr_mul chains (1e9 Fr-mul/s) */
 int gkrb200_microbench(gkrb200_ctx *ctx, int kind, int iters, double *rate_out, double *ms_out);

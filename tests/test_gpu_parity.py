@@ -295,3 +295,62 @@ def test_gkr_2pow16_full_size_properties(ctx, oracle):
     assert oracle.gkr_verify_mimc(proof.to_vec(), key, msg, a.outputs, qprime) == 0
     assert np.array_equal(proof.Claims[1][0], oracle.evaluate(msg, proof.QPrimes[1][0]))
     assert np.array_equal(proof.Claims[2][45], oracle.evaluate(key, proof.QPrimes[2][45]))
+
+
+# ----------------------------------------------------------------------------- factored cipher round (k_round_cf)
+@pytest.mark.parametrize("bn", [1, 2, 3, 5, 8, 11, 14, 16])
+@pytest.mark.parametrize("par8_max", [0, 16, 1 << 20])
+def test_sumcheck_cipher_factored_random_tables(ctx, oracle, bn, par8_max):
+    """single-claim cipher sumcheck on random tables: the factored coefficient-sum kernel (one thread per pair and
+    eight lanes per pair) against the oracle's restatement of sumcheck/prover.go + algo.go, every word"""
+    import gkrb200
+    rng = np.random.default_rng(1000 + bn)
+    n = 1 << bn
+    L, R, q, ark = rand_fr(rng, n), rand_fr(rng, n), rand_fr(rng, bn).reshape(1, bn, 4), rand_fr(rng, 1)[0]
+    ctx.set_option(ctx.OPT_PAR8_MAX_PAIRS, par8_max)
+    try:
+        for claims in (None, rand_fr(rng, 1)):  # the claim is not trusted by the standalone API (and may be garbage)
+            proof, chal, fin = gkrb200.sumcheck.Prove(ctx, [L, R], q, claims, gkrb200.gates.CipherGate(ark))
+            eproof, echal, efin = oracle.sumcheck_prove([L, R], q, claims, oracle.GATE_CIPHER, ark)
+            assert np.array_equal(proof, eproof)
+            assert np.array_equal(chal, echal)
+            assert np.array_equal(fin, efin)
+    finally:
+        ctx.set_option(ctx.OPT_PAR8_MAX_PAIRS, 8192)
+
+
+@pytest.mark.parametrize("bn", [1, 4, 9])
+def test_sumcheck_cipher_factored_degenerate_challenges(ctx, oracle, bn):
+    """q_k in {0, 1}: no inverse of q_k (0) / eq factor vanishes (1); the prover must fall back to 8 device sums"""
+    import gkrb200
+    rng = np.random.default_rng(2000 + bn)
+    n = 1 << bn
+    L, R, ark = rand_fr(rng, n), rand_fr(rng, n), rand_fr(rng, 1)[0]
+    q = rand_fr(rng, bn)
+    q[0] = 0
+    if bn > 2:
+        q[2] = gkrb200.common.SetUint64([1])[0]
+        q[bn - 1] = 0
+    q = q.reshape(1, bn, 4)
+    proof, chal, fin = gkrb200.sumcheck.Prove(ctx, [L, R], q, None, gkrb200.gates.CipherGate(ark))
+    eproof, echal, efin = oracle.sumcheck_prove([L, R], q, None, oracle.GATE_CIPHER, ark)
+    assert np.array_equal(proof, eproof) and np.array_equal(chal, echal) and np.array_equal(fin, efin)
+
+
+@pytest.mark.parametrize("bn", [0, 1, 4, 10, 13])
+def test_gkr_generic_and_factored_kernels_agree(ctx, oracle, bn):
+    """the evaluate-at-9-points kernel (direct restatement of getPartialPolyChunk) and the factored kernel give the same bytes"""
+    import gkrb200
+    rng = np.random.default_rng(3000 + bn)
+    key, msg, qprime = rand_fr(rng, 1 << bn), rand_fr(rng, 1 << bn), rand_fr(rng, bn)
+    c = gkrb200.MimcCircuit(ctx)
+    a = c.Assign(key, msg)
+    fast = gkrb200.gkr.Prove(c, a, qprime).to_vec()
+    ctx.set_option(ctx.OPT_GENERIC_CIPHER, 1)
+    try:
+        slow = gkrb200.gkr.Prove(c, a, qprime).to_vec()
+    finally:
+        ctx.set_option(ctx.OPT_GENERIC_CIPHER, 0)
+    assert np.array_equal(fast, slow)
+    if bn <= 10:
+        assert np.array_equal(fast, oracle.assign_and_prove_mimc(key, msg, qprime)[1])
