@@ -87,6 +87,7 @@ static constexpr int MAX_CLAIMS = 91;
 static constexpr int ROUND_BLOCK = 128;
 static constexpr int ROUND_MINB = 5;  // resident blocks per SM the round kernels are compiled for
 static constexpr int MAX_EV = 9;
+static constexpr int TAIL_MAX_FWD = 32;
 
 static inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -112,12 +113,13 @@ struct gkrb200_ctx {
     FrRaw* partials = nullptr;   // [max_grid][MAX_EV]
     unsigned int* ticket = nullptr;
     FrRaw* d_local = nullptr;    // [32] this rank's contribution (multi-GPU); [16..19) residual entries of the last fold
-    FrRaw* d_all = nullptr;      // [8*16]
+    FrRaw* d_all = nullptr;      // [8*32]
+    FrRaw* d_resid = nullptr;    // [3][TAIL_MAX] residual tables after the last device fold
     uint32_t* partials_w = nullptr;  // [max_grid][8][9] per-block 288-bit sums of the factored cipher round
     int max_grid = 0;
 
     // pinned, device-mapped result slot
-    FrRaw* h_result = nullptr;  // [128] (4 KiB: 8 ranks x 8 wide sums x 36 B fit)
+    FrRaw* h_result = nullptr;  // [256] (8 KiB: 8 ranks x 8 wide sums x 9 tagged 64-bit words fit)
     volatile uint32_t* h_flag = nullptr;
     uint32_t seq = 0;
     H::Fr* h_stage = nullptr;  // pinned staging for qprimes/mults uploads [MAX_CLAIMS*(max_bn+1)]
@@ -153,6 +155,7 @@ struct gkrb200_ctx {
     void prof_begin(int cls);
     void prof_end();
     int wait_flag(uint32_t seq);
+    int wait_words(uint32_t seq, size_t n_words);
     int upload(FrRaw* dst, const void* src, size_t n_elems);
 
     int build_eq(const H::Fr* qprimes, size_t n_q, int bn_local, const H::Fr* mults, FrRaw* out);
@@ -163,6 +166,8 @@ struct gkrb200_ctx {
     bool force_generic = false;  // test hook: run cipher layers through the generic evaluate-at-9-points kernel
     int exchange_and_fetch(int nacc, H::Fr* out);
     int exchange_and_fetch_wide(int nm, H::Fr* out);
+    int fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX_FWD]);
+    int tail_len = TAIL_MAX_FWD;     // option: residual length (entries over all ranks) handed to the host
     int sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn_total, const H::Fr* q, const H::Fr* trusted_claim, const H::Fr& ark, bool use_shards,
                     H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out);
 };
@@ -231,6 +236,31 @@ int gkrb200_ctx::wait_flag(uint32_t want) {
     return 0;
 }
 
+// spin until every tagged 64-bit word of h_result carries `want` in its upper half (see publish_word in kernels.cuh)
+int gkrb200_ctx::wait_words(uint32_t want, size_t n_words) {
+    const double t0 = now_ms();
+    const volatile uint64_t* w = (const volatile uint64_t*)h_result;
+    unsigned spins = 0;
+    for (;;) {
+        bool all = true;
+        for (size_t i = n_words; i-- > 0;)  // the last word usually lands last
+            if ((uint32_t)(w[i] >> 32) != want) {
+                all = false;
+                break;
+            }
+        if (all) break;
+        _mm_pause();
+        if ((++spins & 0xfff) == 0) {
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(GKRB200_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(q));
+            if (now_ms() - t0 > 60000.0) return fail(GKRB200_ERR_CUDA, "timeout waiting for device result %u", want);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    st.wait_ms += now_ms() - t0;
+    return 0;
+}
+
 int gkrb200_ctx::upload(FrRaw* dst, const void* src, size_t n_elems) {
     st.h2d_bytes += n_elems * sizeof(FrRaw);
     CUDA_TRY(cudaMemcpyAsync(dst, src, n_elems * sizeof(FrRaw), cudaMemcpyHostToDevice, stream));
@@ -248,6 +278,7 @@ static inline int grid_for(size_t work_items, int block, int max_grid) {
 // ------------------------------------------------------------------------------------------------ factored cipher round: launch plumbing
 static constexpr int CF_BLOCK = 128;
 static constexpr int CF_MINB = 4;
+static constexpr size_t CF_SMEM_PAR8 = (8 * 9 + (CF_BLOCK / 32) * 8 * 9 + (CF_BLOCK / 8) * 8 * 9) * 4;
 
 typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
 static cf_kernel_t cf_kernel(bool fold, int nm, bool par8) {
@@ -266,11 +297,11 @@ static int set_cf_attrs() {
     return 0;
 }
 
-// 288-bit plain sums (one per rank) -> canonical field element
-static H::Fr wide_to_fr(const uint32_t* w, int n_ranks, size_t rank_stride_words) {
+// 288-bit plain sums (one per rank; tagged 64-bit words, limb in the low half) -> canonical field element
+static H::Fr wide_to_fr(const volatile uint64_t* w, int n_ranks, size_t rank_stride_words) {
     uint64_t acc[10] = {0};
     for (int g = 0; g < n_ranks; g++)
-        for (int l = 0; l < 9; l++) acc[l] += w[(size_t)g * rank_stride_words + l];
+        for (int l = 0; l < 9; l++) acc[l] += (uint32_t)w[(size_t)g * rank_stride_words + l];
     for (int l = 0; l < 9; l++) {  // carry-normalise to 32-bit limbs
         acc[l + 1] += acc[l] >> 32;
         acc[l] &= 0xffffffffu;
@@ -321,7 +352,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     const int nsmall = (max_bn + 1) / 2;
     const size_t small = (size_t)1 << nsmall;
     size_t total = 93 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
-                   (size_t)c->max_grid * MAX_EV + 32 + 8 * 16 + 64 + ((size_t)c->max_grid * 8 * 9 * 4 + 31) / 32;
+                   (size_t)c->max_grid * MAX_EV + 32 + 8 * 32 + 3 * 32 + 64 + ((size_t)c->max_grid * 8 * 9 * 4 + 31) / 32;
     cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
     if (me != cudaSuccess) {
         delete c;
@@ -337,12 +368,14 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     c->d_mults = p; p += MAX_CLAIMS;
     c->partials = p; p += (size_t)c->max_grid * MAX_EV;
     c->d_local = p; p += 32;
-    c->d_all = p; p += 8 * 16;
+    c->d_all = p; p += 8 * 32;
+    c->d_resid = p; p += 3 * 32;
     c->partials_w = (uint32_t*)p; p += ((size_t)c->max_grid * 8 * 9 * 4 + 31) / 32;
     CUDA_TRY(cudaMalloc(&c->ticket, 64));
     CUDA_TRY(cudaMemset(c->ticket, 0, 64));
-    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 128 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
-    c->h_flag = (volatile uint32_t*)(c->h_result + 128);
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 256 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
+    memset(c->h_result, 0, 256 * sizeof(FrRaw) + 64);
+    c->h_flag = (volatile uint32_t*)(c->h_result + 256);
     *c->h_flag = 0;
     CUDA_TRY(cudaHostAlloc((void**)&c->h_stage, (size_t)MAX_CLAIMS * (max_bn + 2) * sizeof(H::Fr), cudaHostAllocDefault));
     // opt in to the dynamic shared memory the round kernels need
@@ -547,6 +580,86 @@ static void host_fold(H::Fr* t, size_t len, const H::Fr& r) {
     for (size_t i = 0; i < mid; i++) t[i] = H::add(t[i], H::mul(r, H::sub(t[i + mid], t[i])));
 }
 
+// poly/eq.go:41-59 FoldedEqTable on the host (tiny tables of the tail), seeded with `seed`
+static void host_eq_table(const H::Fr* q, int n, const H::Fr& seed, H::Fr* out) {
+    out[0] = seed;
+    for (int i = 0; i < n; i++) {
+        const size_t step = (size_t)1 << (n - 1 - i);
+        for (size_t j = 0; j < ((size_t)1 << i); j++) {
+            const size_t J = j << (n - i);
+            out[J + step] = H::mul(q[i], out[J]);
+            out[J] = H::sub(out[J], out[J + step]);
+        }
+    }
+}
+
+static constexpr int TAIL_MAX = TAIL_MAX_FWD;  // largest residual table (entries, all ranks together) finished on the host
+
+// Rounds k0..bn-1 on the host over the gathered residual tables of length rl = 2^(bn-k0) (at most TAIL_MAX entries):
+// below that size a device round trip (launch + PCIe latency) costs more than the handful of multiplications.
+// Same per-round steps as the device rounds: evaluate at 0..deg (sumcheck/algo.go:54-205), InterpolateOnRange,
+// GetChallenge, Fold.  Leaves [Eq(r), X0(r), X1(r)] in final_out.
+static void host_tail(const H::Lagrange& lagrange, H::Fr* te, H::Fr* t0v, H::Fr* t1v, size_t rl, int gate, const H::Fr& ark, int k0, int bn,
+                      H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out, gkrb200_stats& st) {
+    const int nev = gate == gkr::GATE_CIPHER ? 9 : 3;
+    const int nin = gate == gkr::GATE_CIPHER ? 2 : 1;
+    H::Fr evals[MAX_EV];
+    for (int k = k0; k < bn; k++) {
+        const double t0 = now_ms();
+        host_round_eval(te, t0v, t1v, rl, gate, ark, evals);
+        H::Fr* coeffs = proof_out + (size_t)k * nev;
+        lagrange.interpolate(evals, nev, coeffs);
+        const H::Fr r = H::mimc_hash(coeffs, nev);
+        challenges_out[k] = r;
+        host_fold(te, rl, r);
+        host_fold(t0v, rl, r);
+        if (nin > 1) host_fold(t1v, rl, r);
+        rl /= 2;
+        st.transcript_ms += now_ms() - t0;
+        st.rounds++;
+    }
+    final_out[0] = te[0];
+    final_out[1] = t0v[0];
+    if (nin > 1) final_out[2] = t1v[0];
+}
+
+// Residual tables for the host tail.  cur[t] (t < ntab) are this rank's device tables; when folded_by_r they have length
+// 2*lres and are folded once more with r (the last device challenge), otherwise they have length lres and are taken as is.
+// tabs[t][0 .. lres*W) receives the global residual table: entry j*W + g = rank g's entry j (strided sharding).
+int gkrb200_ctx::fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX]) {
+    if (folded_by_r) {
+        gkr::FoldArgs f{};
+        f.n_tables = ntab;
+        for (int i = 0; i < ntab; i++) {
+            f.src[i] = cur[i];
+            f.dst[i] = d_resid + (size_t)i * lres;
+        }
+        f.half = lres;
+        memcpy(&f.r, &r, 32);
+        LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 128, 0, f);
+    } else {
+        for (int i = 0; i < ntab; i++)
+            CUDA_TRY(cudaMemcpyAsync(d_resid + (size_t)i * lres, cur[i], lres * sizeof(FrRaw), cudaMemcpyDeviceToDevice, stream));
+    }
+    const size_t per_rank = (size_t)ntab * lres;
+    const FrRaw* src = d_resid;
+    if (W > 1) {
+        const double t0 = now_ms();
+        NCCL_TRY(g_nccl.AllGather(d_resid, d_all, per_rank * sizeof(FrRaw), ncclUint8, comm, stream));
+        st.comm_ms += now_ms() - t0;
+        src = d_all;
+    }
+    CUDA_TRY(cudaMemcpyAsync(h_stage, src, per_rank * (size_t)W * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
+    const double t1 = now_ms();
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    st.wait_ms += now_ms() - t1;
+    st.d2h_bytes += per_rank * (size_t)W * sizeof(FrRaw);
+    for (int g = 0; g < W; g++)
+        for (int t = 0; t < ntab; t++)
+            for (size_t j = 0; j < lres; j++) tabs[t][j * (size_t)W + g] = h_stage[((size_t)g * ntab + t) * lres + j];
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ sumcheck.Prove
 // x0/x1: device tables of this rank (n_local = 2^(bn_total - log_world) entries when use_shards), never modified.
 // qprimes: n_q * bn_total.  Returns bn_total*(nev) coefficients, bn_total challenges, 1+arity final claims.
@@ -613,7 +726,11 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
     size_t len = n_local;
     H::Fr evals[MAX_EV], r = H::zero();
     FrRaw* result_dev = W > 1 ? d_local : h_result;
-    for (int k = 0; k < bnl; k++) {
+    // the last rounds (residual table of at most tail_len entries over all ranks) are finished on the host
+    int tail_bits = 0;
+    while (((size_t)2 << tail_bits) * (size_t)W <= (size_t)tail_len && tail_bits < bnl) tail_bits++;
+    const int kdev = bnl - tail_bits;
+    for (int k = 0; k < kdev; k++) {
         gkr::RoundArgs a{};
         const bool do_fold = k > 0;
         const size_t half = len / (do_fold ? 4 : 2);
@@ -657,70 +774,12 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         st.transcript_ms += now_ms() - t0;
         st.rounds++;
     }
-    // ---- last fold on the device: tables of length 2 -> the rank's residual entries [eq, x0, x1]
-    H::Fr resid[3];
-    if (bnl > 0) {
-        gkr::FoldArgs f{};
-        f.n_tables = 1 + nin;
-        for (int i = 0; i < 1 + nin; i++) {
-            f.src[i] = cur[i];
-            f.dst[i] = d_local + 16 + i;
-        }
-        f.half = 1;
-        memcpy(&f.r, &r, 32);
-        LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 32, 0, f);
-        CUDA_TRY(cudaMemcpyAsync(h_stage, d_local + 16, (1 + nin) * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        memcpy(resid, h_stage, (1 + nin) * sizeof(H::Fr));
-        st.d2h_bytes += (1 + nin) * sizeof(H::Fr);
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(h_stage, eq, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaMemcpyAsync(h_stage + 1, x0, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-        if (nin > 1) CUDA_TRY(cudaMemcpyAsync(h_stage + 2, x1, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        memcpy(resid, h_stage, (1 + nin) * sizeof(H::Fr));
-    }
-    if (W == 1) {
-        for (int i = 0; i < 1 + nin; i++) final_out[i] = resid[i];
-        return 0;
-    }
-    // ---- sharded: gather the residual world-entry tables (entry g = rank g's value) and finish on the host
-    {
-        const double t0 = now_ms();
-        memcpy(h_stage, resid, 3 * sizeof(H::Fr));
-        TRY(upload(d_local, h_stage, 3));
-        NCCL_TRY(g_nccl.AllGather(d_local, d_all, 3 * sizeof(FrRaw), ncclUint8, comm, stream));
-        CUDA_TRY(cudaMemcpyAsync(h_stage + 4, d_all, (size_t)W * 3 * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        st.comm_ms += now_ms() - t0;
-    }
-    H::Fr te[8], t0v[8], t1v[8];
-    for (int g = 0; g < W; g++) {
-        te[g] = h_stage[4 + 3 * g];
-        t0v[g] = h_stage[4 + 3 * g + 1];
-        t1v[g] = h_stage[4 + 3 * g + 2];
-    }
-    size_t rl = (size_t)W;
-    for (int k = bnl; k < bn; k++) {
-        const double t0 = now_ms();
-        host_round_eval(te, t0v, t1v, rl, gate, ark, evals);
-        H::Fr* coeffs = proof_out + (size_t)k * nev;
-        lagrange.interpolate(evals, nev, coeffs);
-        r = H::mimc_hash(coeffs, nev);
-        challenges_out[k] = r;
-        host_fold(te, rl, r);
-        host_fold(t0v, rl, r);
-        if (nin > 1) host_fold(t1v, rl, r);
-        rl /= 2;
-        st.transcript_ms += now_ms() - t0;
-        st.rounds++;
-    }
-    final_out[0] = te[0];
-    final_out[1] = t0v[0];
-    if (nin > 1) final_out[2] = t1v[0];
+    // ---- residual tables (folded with the last device challenge) -> host, gathered over the ranks; host finishes
+    H::Fr tabs[3][TAIL_MAX];
+    TRY(fetch_residual(cur, 1 + nin, (size_t)1 << tail_bits, kdev > 0, r, W, tabs));
+    host_tail(lagrange, tabs[0], tabs[1], tabs[2], ((size_t)1 << tail_bits) * (size_t)W, gate, ark, kdev, bn, proof_out, challenges_out, final_out, st);
     return 0;
 }
-
 
 // Wide variant for the factored cipher round: nm 288-bit sums per rank.
 int gkrb200_ctx::exchange_and_fetch_wide(int nm, H::Fr* out) {
@@ -728,16 +787,16 @@ int gkrb200_ctx::exchange_and_fetch_wide(int nm, H::Fr* out) {
     const size_t words = (size_t)nm * 9;
     if (W > 1) {
         const double t0 = now_ms();
-        NCCL_TRY(g_nccl.AllGather(d_local, d_all, words * 4, ncclUint8, comm, stream));
+        NCCL_TRY(g_nccl.AllGather(d_local, d_all, words * 8, ncclUint8, comm, stream));
         st.launches_total++;
         st.launches[KC_MISC]++;
-        gkr::k_publish_words<<<1, 128, 0, stream>>>((const uint32_t*)d_all, (int)(words * W), (uint32_t*)h_result, h_flag, seq);
+        gkr::k_publish_words<<<1, 128, 0, stream>>>((const unsigned long long*)d_all, (int)(words * W), (unsigned long long*)h_result);
         st.comm_ms += now_ms() - t0;
     }
-    TRY(wait_flag(seq));
-    const uint32_t* w = (const uint32_t*)h_result;
+    TRY(wait_words(seq, words * (size_t)W));
+    const volatile uint64_t* w = (const volatile uint64_t*)h_result;
     for (int i = 0; i < nm; i++) out[i] = wide_to_fr(w + (size_t)i * 9, W, words);
-    st.d2h_bytes += words * 4 * (size_t)W + 4;
+    st.d2h_bytes += words * 8 * (size_t)W;
     return 0;
 }
 
@@ -787,7 +846,10 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         seed_all[g] = sd;
     }
     const int c = bnl / 2;  // variables in the low suffix table
-    if (bnl > 0) {
+    int tail_bits = 0;  // the last rounds (residual table of at most tail_len entries over all ranks) are finished on the host
+    while (((size_t)2 << tail_bits) * (size_t)W <= (size_t)tail_len && tail_bits < bnl) tail_bits++;
+    const int kdev = bnl - tail_bits;
+    if (kdev > 0) {
         gkr::EqSuffixArgs ea{};
         memcpy(ea.q, q, (size_t)bnl * 32);
         memcpy(&ea.seed, &seed_all[W > 1 ? rank : 0], 32);
@@ -807,7 +869,7 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
     H::Fr ck = one, cl = trusted_claim ? *trusted_claim : H::zero(), r = H::zero();
     bool have_cl = trusted_claim != nullptr;
     H::Fr m[8], sc[8];
-    for (int k = 0; k < bnl; k++) {
+    for (int k = 0; k < kdev; k++) {
         const int mk = bnl - 1 - k;  // variables of x'
         const size_t half = (size_t)1 << mk;
         const bool do_fold = k > 0;
@@ -832,11 +894,10 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         ++seq;
         a.red.partials = partials_w;
         a.red.ticket = ticket;
-        a.red.result = W > 1 ? (uint32_t*)d_local : (uint32_t*)h_result;
-        a.red.flag = W > 1 ? nullptr : h_flag;
+        a.red.result = W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result;
         a.red.seq = seq;
-        const int grid = grid_for(par8 ? half * 8 : half, CF_BLOCK, max_grid);
-        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, CF_BLOCK, (size_t)nm * 9 * CF_BLOCK * 4, a);
+        const int grid = grid_for(par8 ? half * 8 : half, CF_BLOCK, n_sm * CF_MINB);  // at most one resident wave
+        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, CF_BLOCK, par8 ? CF_SMEM_PAR8 : (size_t)nm * 9 * CF_BLOCK * 4, a);
         CUDA_TRY(cudaGetLastError());
         st.fr_mul_round += (uint64_t)half * ((nm == 8 ? 20 : 18) + (mk > c ? 1 : 0) + (do_fold ? 4 : 0));
         st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
@@ -872,65 +933,12 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         st.transcript_ms += now_ms() - t0;
         st.rounds++;
     }
-    // ---- last fold on the device: tables of length 2 -> this rank's residual entries of X0, X1
-    H::Fr resid[3];
-    resid[0] = H::mul(ck, seed_all[W > 1 ? rank : 0]);
-    if (bnl > 0) {
-        gkr::FoldArgs f{};
-        f.n_tables = 2;
-        for (int i = 0; i < 2; i++) {
-            f.src[i] = cur[i];
-            f.dst[i] = d_local + 16 + i;
-        }
-        f.half = 1;
-        memcpy(&f.r, &r, 32);
-        LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 32, 0, f);
-        CUDA_TRY(cudaMemcpyAsync(h_stage, d_local + 16, 2 * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-    } else {
-        CUDA_TRY(cudaMemcpyAsync(h_stage, x0, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaMemcpyAsync(h_stage + 1, x1, sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-    }
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    memcpy(resid + 1, h_stage, 2 * sizeof(H::Fr));
-    st.d2h_bytes += 2 * sizeof(H::Fr);
-    if (W == 1) {
-        for (int i = 0; i < 3; i++) final_out[i] = resid[i];
-        return 0;
-    }
-    // ---- sharded: gather the residual X entries (entry g = rank g's value); the eq residuals are closed-form
-    {
-        const double t0 = now_ms();
-        memcpy(h_stage, resid + 1, 2 * sizeof(H::Fr));
-        TRY(upload(d_local, h_stage, 2));
-        NCCL_TRY(g_nccl.AllGather(d_local, d_all, 2 * sizeof(FrRaw), ncclUint8, comm, stream));
-        CUDA_TRY(cudaMemcpyAsync(h_stage + 4, d_all, (size_t)W * 2 * sizeof(FrRaw), cudaMemcpyDeviceToHost, stream));
-        CUDA_TRY(cudaStreamSynchronize(stream));
-        st.comm_ms += now_ms() - t0;
-    }
-    H::Fr te[8], t0v[8], t1v[8], evals[MAX_EV];
-    for (int g = 0; g < W; g++) {
-        te[g] = H::mul(ck, seed_all[g]);
-        t0v[g] = h_stage[4 + 2 * g];
-        t1v[g] = h_stage[4 + 2 * g + 1];
-    }
-    size_t rl = (size_t)W;
-    for (int k = bnl; k < bn; k++) {
-        const double t0 = now_ms();
-        host_round_eval(te, t0v, t1v, rl, gkr::GATE_CIPHER, ark, evals);
-        H::Fr* coeffs = proof_out + (size_t)k * 9;
-        lagrange.interpolate(evals, 9, coeffs);
-        r = H::mimc_hash(coeffs, 9);
-        challenges_out[k] = r;
-        host_fold(te, rl, r);
-        host_fold(t0v, rl, r);
-        host_fold(t1v, rl, r);
-        rl /= 2;
-        st.transcript_ms += now_ms() - t0;
-        st.rounds++;
-    }
-    final_out[0] = te[0];
-    final_out[1] = t0v[0];
-    final_out[2] = t1v[0];
+    // ---- residual X tables -> host (gathered over the ranks); the eq residual is closed-form: c_kdev * eq(q[kdev:], .)
+    H::Fr tabs[3][TAIL_MAX];
+    TRY(fetch_residual(cur, 2, (size_t)1 << tail_bits, kdev > 0, r, W, tabs + 1));
+    host_eq_table(q + kdev, bn - kdev, ck, tabs[0]);
+    host_tail(lagrange, tabs[0], tabs[1], tabs[2], ((size_t)1 << tail_bits) * (size_t)W, gkr::GATE_CIPHER, ark, kdev, bn, proof_out, challenges_out,
+              final_out, st);
     return 0;
 }
 
@@ -1176,6 +1184,10 @@ extern "C" int gkrb200_set_option(gkrb200_ctx* c, int option, long value) {
     if (!c) return fail(GKRB200_ERR_ARG, "null context");
     switch (option) {
         case GKRB200_OPT_GENERIC_CIPHER: c->force_generic = value != 0; return 0;
+        case GKRB200_OPT_HOST_TAIL_LEN:
+            if (value < 1 || value > TAIL_MAX || (value & (value - 1))) return fail(GKRB200_ERR_ARG, "host tail length must be a power of two in 1..%d", TAIL_MAX);
+            c->tail_len = (int)value;
+            return 0;
         case GKRB200_OPT_PAR8_MAX_PAIRS:
             if (value < 0) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
             c->par8_max_pairs = (size_t)value;
@@ -1183,6 +1195,12 @@ extern "C" int gkrb200_set_option(gkrb200_ctx* c, int option, long value) {
         default: return fail(GKRB200_ERR_ARG, "unknown option %d", option);
     }
 }
+
+#ifdef GKR_TRACE
+extern "C" int gkrb200_trace_get(long long* out16) {
+    return cudaMemcpyFromSymbol(out16, gkr::g_trace, 16 * sizeof(long long)) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, double* rate_out, double* ms_out) {
     // low byte: kind; next byte (optional): warps per SM to allow (occupancy limited through dynamic shared memory)

@@ -414,20 +414,109 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round(const RoundArgs a) {
 // with a uniform select-and-multiply ladder) so that small rounds are not bound by one thread's chain
 // of ~23 dependent multiplications.
 // ================================================================================================
+#ifdef GKR_TRACE
+__device__ long long g_trace[16];
+#define GKR_T(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_trace[i] = clock64(); } while (0)
+#else
+#define GKR_T(i) do { } while (0)
+#endif
+
 struct WideOut {
-    uint32_t* partials;       // [gridDim.x][NM][9] device scratch
-    unsigned int* ticket;     // device counter, zero between launches
-    uint32_t* result;         // NM x 9 words (288-bit plain sums, NOT reduced); device or mapped host memory
-    volatile uint32_t* flag;  // optional: set to seq once result is visible system-wide
-    uint32_t seq;
+    uint32_t* partials;            // [gridDim.x][NM][9] device scratch
+    unsigned int* ticket;          // device counter, zero between launches
+    unsigned long long* result;    // NM x 9 words, each (seq << 32) | limb of a 288-bit plain sum (NOT reduced mod q);
+                                   // device memory or mapped host memory
+    uint32_t seq;                  // tag of this launch: the consumer polls until every word carries it
 };
 
-// Block tree over the per-thread 288-bit accumulators, then (grid > 1) a last-block pass over the per-block
-// sums.  No field multiplication anywhere: the host reduces the NM wide sums modulo q.
+// a += b as 288-bit integers (9 x 32-bit limbs)
+__device__ __forceinline__ void wide9_add(uint32_t (&a)[9], const uint32_t (&b)[9]) {
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, %8, %17;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8])
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]));
+}
+
+// Publishing without fences: every 64-bit word carries the launch tag in its upper half and is written with one
+// aligned 8-byte store, so the consumer (host spinning on mapped pinned memory, or a later kernel) needs no flag
+// and no ordering between words -- it waits until all NM*9 words show the tag.  Saves the two system-scope fences
+// (~3 us measured) a flag protocol costs per round.
+__device__ __forceinline__ void publish_word(unsigned long long* dst, uint32_t seq, uint32_t limb) {
+    const unsigned long long v = ((unsigned long long)seq << 32) | limb;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
+}
+
+// Grid stage shared by both layouts of k_round_cf.  tot: this block's NM x 9 limb sums in shared memory
+// (tot[k*9 + l]); scratch: >= (BLOCK/8) * NM * 9 words of shared memory.  No field multiplication anywhere:
+// the host reduces the NM wide sums modulo q.
+template <int NM, int BLOCK>
+__device__ __forceinline__ void grid_stage_wide(const uint32_t* tot, uint32_t* scratch, const WideOut& out) {
+    const int tid = threadIdx.x;
+    __shared__ bool is_last_r;
+    GKR_T(5);
+    if (gridDim.x == 1) {
+        if (tid < NM * 9) publish_word(out.result + tid, out.seq, tot[tid]);
+        GKR_T(6);
+        return;
+    }
+    if (tid < NM * 9) out.partials[(size_t)blockIdx.x * (NM * 9) + tid] = tot[tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last_r = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last_r) return;
+    __threadfence();
+    // last block: lane group (tid >> 3) sums the partials of blocks tid>>3, +BLOCK/8, ... for accumulator tid & 7
+    {
+        const int k = tid & 7, slice = tid >> 3;
+        uint32_t a[9];
+#pragma unroll
+        for (int l = 0; l < 9; l++) a[l] = 0;
+        if (k < NM) {
+#pragma unroll 1
+            for (unsigned b = slice; b < gridDim.x; b += BLOCK / 8) {
+                const uint32_t* pp = out.partials + (size_t)b * (NM * 9) + k * 9;
+                uint32_t w[9];
+#pragma unroll
+                for (int l = 0; l < 9; l++) w[l] = __ldcg(pp + l);
+                wide9_add(a, w);
+            }
+#pragma unroll
+            for (int l = 0; l < 9; l++) scratch[(slice * NM + k) * 9 + l] = a[l];
+        }
+    }
+    __syncthreads();
+    if (tid < NM) {
+        uint32_t a[9];
+#pragma unroll
+        for (int l = 0; l < 9; l++) a[l] = scratch[tid * 9 + l];
+#pragma unroll 1
+        for (int sl = 1; sl < BLOCK / 8; sl++) {
+            uint32_t w[9];
+#pragma unroll
+            for (int l = 0; l < 9; l++) w[l] = scratch[(sl * NM + tid) * 9 + l];
+            wide9_add(a, w);
+        }
+#pragma unroll
+        for (int l = 0; l < 9; l++) publish_word(out.result + tid * 9 + l, out.seq, a[l]);
+    }
+    if (tid == 0) *out.ticket = 0;
+    GKR_T(6);
+}
+
+// PAR = 1 layout: per-thread 288-bit accumulators in shared memory (sm[(k*9+l)*BLOCK + tid]) -> block tree -> grid stage
 template <int NM, int BLOCK>
 __device__ __forceinline__ void grid_reduce_wide_raw(uint32_t* sm, const WideOut& out) {
     const int tid = threadIdx.x;
     __syncthreads();
+    GKR_T(4);
 #pragma unroll 1
     for (int stride = BLOCK / 2; stride >= 1; stride >>= 1) {
         const int items = NM * stride;
@@ -438,66 +527,13 @@ __device__ __forceinline__ void grid_reduce_wide_raw(uint32_t* sm, const WideOut
         }
         __syncthreads();
     }
-    __shared__ bool is_last_r;
-    if (gridDim.x == 1) {
-        if (tid < NM * 9) out.result[tid] = sm[tid * BLOCK];
-    } else {
-        if (tid < NM * 9) out.partials[(size_t)blockIdx.x * (NM * 9) + tid] = sm[tid * BLOCK];
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) is_last_r = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
-        __syncthreads();
-        if (!is_last_r) return;
-        __threadfence();
-        // last block: thread t sums the partials of blocks t, t+BLOCK, ... for every accumulator, then the tree again
-#pragma unroll 1
-        for (int k = 0; k < NM; k++) {
-            uint32_t a[9];
-#pragma unroll
-            for (int l = 0; l < 9; l++) a[l] = 0;
-#pragma unroll 1
-            for (unsigned b = tid; b < gridDim.x; b += BLOCK) {
-                const uint32_t* pp = out.partials + (size_t)b * (NM * 9) + k * 9;
-                uint32_t w[9];
-#pragma unroll
-                for (int l = 0; l < 9; l++) w[l] = __ldcg(pp + l);
-                asm("add.cc.u32 %0, %0, %9;\n\t"
-                    "addc.cc.u32 %1, %1, %10;\n\t"
-                    "addc.cc.u32 %2, %2, %11;\n\t"
-                    "addc.cc.u32 %3, %3, %12;\n\t"
-                    "addc.cc.u32 %4, %4, %13;\n\t"
-                    "addc.cc.u32 %5, %5, %14;\n\t"
-                    "addc.cc.u32 %6, %6, %15;\n\t"
-                    "addc.cc.u32 %7, %7, %16;\n\t"
-                    "addc.u32 %8, %8, %17;"
-                    : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8])
-                    : "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]), "r"(w[8]));
-            }
-#pragma unroll
-            for (int l = 0; l < 9; l++) sm[(k * 9 + l) * BLOCK + tid] = a[l];
-        }
-        __syncthreads();
-#pragma unroll 1
-        for (int stride = BLOCK / 2; stride >= 1; stride >>= 1) {
-            const int items = NM * stride;
-#pragma unroll 1
-            for (int it = tid; it < items; it += BLOCK) {
-                const int k = it / stride, i = it - k * stride;
-                wide_pair_add<BLOCK>(sm, k, i, stride);
-            }
-            __syncthreads();
-        }
-        if (tid < NM * 9) out.result[tid] = sm[tid * BLOCK];
-        if (tid == 0) *out.ticket = 0;
-    }
-    if (out.flag) {
-        if (tid < NM * 9) __threadfence_system();  // publish this thread's result word before the barrier
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            *out.flag = out.seq;
-        }
-    }
+    // compact the block totals (column 0 of every row) to the front, then reuse the rest as scratch
+    uint32_t v = 0;
+    if (tid < NM * 9) v = sm[tid * BLOCK];
+    __syncthreads();
+    if (tid < NM * 9) sm[tid] = v;
+    __syncthreads();
+    grid_stage_wide<NM, BLOCK>(sm, sm + NM * 9, out);
 }
 
 // Suffix eq tables of one layer's challenge vector q[0..n): block 0 builds the stages of the low part
@@ -560,8 +596,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
     static_assert(PAR == 1 || PAR == 8, "one thread or eight lanes per pair");
     extern __shared__ uint32_t sm[];  // NM * 9 * BLOCK words
     const int tid = threadIdx.x;
+    GKR_T(0);
+    if (PAR == 1) {
 #pragma unroll 1
-    for (int i = tid; i < NM * 9 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
+        for (int i = tid; i < NM * 9 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
+    }
+    GKR_T(1);
     const Fr r = fr_unpack(a.r);
     const Fr ark = fr_unpack(a.ark);
     const size_t half = a.half, m2 = 2 * half;
@@ -598,6 +638,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
     } else {
         const int j = tid & 7;
         const size_t pstride = (size_t)gridDim.x * (BLOCK / 8);
+        uint32_t wacc[9];  // this lane's 288-bit sum of term j
+#pragma unroll
+        for (int l = 0; l < 9; l++) wacc[l] = 0;
         // block-uniform trip count (the shuffles below need every lane of the warp); surplus lanes redo pair 0 unrecorded
         for (size_t xb = (size_t)blockIdx.x * (BLOCK / 8); xb < half; xb += pstride) {
             const bool live = xb + (tid >> 3) < half;
@@ -614,6 +657,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
             } else {
                 f = fr_load_stream(a.src[tb] + idx);
             }
+            Fr u = a.tA ? fr_mulc(fr_load(a.tA + (x >> a.c)), fr_load(a.tB + (x & cmask))) : fr_load(a.tB + x);
             Fr f0, f1, f2, f3;
             const int base = (threadIdx.x & 31) & ~7;
 #pragma unroll
@@ -623,34 +667,76 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
                 f2.v[l] = __shfl_sync(0xffffffffu, f.v[l], base + 2);
                 f3.v[l] = __shfl_sync(0xffffffffu, f.v[l], base + 3);
             }
+            GKR_T(2);
             const Fr av = fr_add(fr_add(f0, f2), ark);
             const Fr bv = fr_add(fr_sub(f1, f0), fr_sub(f3, f2));
-            Fr u = a.tA ? fr_mulc(fr_load(a.tA + (x >> a.c)), fr_load(a.tB + (x & cmask))) : fr_load(a.tB + x);
-            const Fr a2 = fr_sqrc(av), b2 = fr_sqrc(bv);
-            const Fr a4 = fr_sqrc(a2), b4 = fr_sqrc(b2);
-            // term j = T * a^(7-j) * b^j : bit i of j selects b^(2^i), otherwise a^(2^i)
+            // term j = T * a^(7-j) * b^j : bit i of j selects b^(2^i), otherwise a^(2^i); every lane squares its OWN base
+            // (lanes with bit i set only ever need powers of b for that bit), so the ladder is 2 squarings + 3 products deep
             Fr s1, s2, s4;
 #pragma unroll
-            for (int l = 0; l < 8; l++) {
-                s1.v[l] = (j & 1) ? bv.v[l] : av.v[l];
-                s2.v[l] = (j & 2) ? b2.v[l] : a2.v[l];
-                s4.v[l] = (j & 4) ? b4.v[l] : a4.v[l];
-            }
+            for (int l = 0; l < 8; l++) s1.v[l] = (j & 1) ? bv.v[l] : av.v[l];
+            Fr w2;
+#pragma unroll
+            for (int l = 0; l < 8; l++) w2.v[l] = (j & 2) ? bv.v[l] : av.v[l];
+            s2 = fr_sqrc(w2);
+            Fr w4;
+#pragma unroll
+            for (int l = 0; l < 8; l++) w4.v[l] = (j & 4) ? bv.v[l] : av.v[l];
+            s4 = fr_sqrc(fr_sqrc(w4));
             u = fr_mulc(fr_mulc(fr_mulc(u, s1), s2), s4);
-            if (live && j < NM) wide_acc_add<BLOCK>(sm + (size_t)j * 9 * BLOCK + tid, u);
+            GKR_T(3);
+            if (live && j < NM) {
+                uint32_t t9[9];
+#pragma unroll
+                for (int l = 0; l < 8; l++) t9[l] = u.v[l];
+                t9[8] = 0;
+                wide9_add(wacc, t9);
+            }
         }
+        // lanes j, j+8, j+16, j+24 hold the same accumulator: fold them, then the warps through shared memory
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+            uint32_t o[9];
+#pragma unroll
+            for (int l = 0; l < 9; l++) o[l] = __shfl_xor_sync(0xffffffffu, wacc[l], off);
+            wide9_add(wacc, o);
+        }
+        constexpr int NW = BLOCK / 32;
+        uint32_t* tot = sm;                  // [8][9] block totals
+        uint32_t* stage = sm + 8 * 9;        // [NW][8][9]
+        const int warp = tid >> 5, lane = tid & 31;
+        GKR_T(4);
+        if (lane < 8) {
+#pragma unroll
+            for (int l = 0; l < 9; l++) stage[(warp * 8 + lane) * 9 + l] = wacc[l];
+        }
+        __syncthreads();
+        if (tid < 8) {
+            uint32_t acc9[9];
+#pragma unroll
+            for (int l = 0; l < 9; l++) acc9[l] = stage[tid * 9 + l];
+#pragma unroll
+            for (int w = 1; w < NW; w++) {
+                uint32_t o[9];
+#pragma unroll
+                for (int l = 0; l < 9; l++) o[l] = stage[(w * 8 + tid) * 9 + l];
+                wide9_add(acc9, o);
+            }
+#pragma unroll
+            for (int l = 0; l < 9; l++) tot[tid * 9 + l] = acc9[l];
+        }
+        __syncthreads();
+        grid_stage_wide<NM, BLOCK>(tot, sm + 8 * 9 + NW * 8 * 9, a.red);
+        return;
     }
     grid_reduce_wide_raw<NM, BLOCK>(sm, a.red);
 }
 
-// copies nwords 32-bit words to (mapped) host memory and raises the flag (multi-GPU: after the all-gather)
-__global__ void k_publish_words(const uint32_t* __restrict__ src, int nwords, uint32_t* dst, volatile uint32_t* flag, uint32_t seq) {
-    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0 && flag) {
-        __threadfence_system();
-        *flag = seq;
+// copies n tagged 64-bit words (see publish_word) to mapped host memory; the tags travel with the data
+__global__ void k_publish_words(const unsigned long long* __restrict__ src, int n, unsigned long long* dst) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long v = src[i];
+        asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst + i), "l"(v) : "memory");
     }
 }
 

@@ -139,6 +139,9 @@ int gkrb200_set_profiling(gkrb200_ctx *ctx, int on);
  * GKRB200_OPT_PAR8_MAX_PAIRS: rounds with at most this many pairs spread one pair over 8 lanes.            */
 #define GKRB200_OPT_GENERIC_CIPHER 1
 #define GKRB200_OPT_PAR8_MAX_PAIRS 2
+/* GKRB200_OPT_HOST_TAIL_LEN (power of two, 1..32, default 32): once the tables of a sumcheck have at most this many
+ * entries (over all ranks) the remaining rounds run on the host -- a device round trip costs more than they do.   */
+#define GKRB200_OPT_HOST_TAIL_LEN 3
 int gkrb200_set_option(gkrb200_ctx *ctx, int option, long value);
 
 /* integer-pipe microbenchmarks for the roofline denominator: returns achieved rate.

@@ -354,3 +354,30 @@ def test_gkr_generic_and_factored_kernels_agree(ctx, oracle, bn):
     assert np.array_equal(fast, slow)
     if bn <= 10:
         assert np.array_equal(fast, oracle.assign_and_prove_mimc(key, msg, qprime)[1])
+
+
+@pytest.mark.parametrize("tail_len", [1, 4, 32])
+def test_host_tail_length_does_not_change_the_proof(ctx, oracle, tail_len):
+    """the rounds finished on the host (residual tables <= tail_len entries) give the same bytes as device rounds"""
+    import gkrb200
+    c = gkrb200.MimcCircuit(ctx)
+    ctx.set_option(ctx.OPT_HOST_TAIL_LEN, tail_len)
+    try:
+        for bn in (0, 1, 2, 3, 5, 6, 9):
+            rng = np.random.default_rng(4000 + bn)
+            key, msg, qprime = rand_fr(rng, 1 << bn), rand_fr(rng, 1 << bn), rand_fr(rng, bn)
+            a = c.Assign(key, msg)
+            assert np.array_equal(gkrb200.gkr.Prove(c, a, qprime).to_vec(), oracle.assign_and_prove_mimc(key, msg, qprime)[1]), bn
+            # standalone sumchecks: identity with 3 claims and cipher, same option
+            n = 1 << bn
+            qs = rand_fr(rng, 3 * bn).reshape(3, bn, 4)
+            L, R, ark = rand_fr(rng, n), rand_fr(rng, n), rand_fr(rng, 1)[0]
+            claims = rand_fr(rng, 3)
+            got = gkrb200.sumcheck.Prove(ctx, [L], qs, claims, gkrb200.gates.IdentityGate())
+            exp = oracle.sumcheck_prove([L], qs, claims, oracle.GATE_IDENTITY, None)
+            assert all(np.array_equal(g, e) for g, e in zip(got, exp)), bn
+            got = gkrb200.sumcheck.Prove(ctx, [L, R], qs[:1], None, gkrb200.gates.CipherGate(ark))
+            exp = oracle.sumcheck_prove([L, R], qs[:1], None, oracle.GATE_CIPHER, ark)
+            assert all(np.array_equal(g, e) for g, e in zip(got, exp)), bn
+    finally:
+        ctx.set_option(ctx.OPT_HOST_TAIL_LEN, 32)
