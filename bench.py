@@ -131,11 +131,17 @@ def run_reference(args, rank, world):
     return 0
 
 
-def workload_config(args, world):
+# dram__bytes_read.sum + dram__bytes_write.sum of the largest k_round_cf launches (ncu --set full, profiles/r1_ncu_k_round_cf_v3_bn22.txt):
+# round 0 (2^21 pairs, no fold) 272.7 MB vs 268.4 MB algorithmic; round 1 (2^20 pairs, fold) 377.7 MB vs 402.7 MB algorithmic
+NCU_TRAFFIC = {22: 272.7e6}
+NCU_TRAFFIC_NOTE = "ncu capture of the round-0 launch of one layer (2^21 pairs: 268.4 MB algorithmic); `achieved` averages all 1564 launches of a proof"
+
+
+def workload_config(args, world, P=1):
     return {
         "workload": "full MiMC GKR proof (Circuit.Assign + gkr.Prove, 94 layers, transcript bit-exact) of a 2^%d-hash batch over BN254 Fr" % args.bn,
         "bn": args.bn, "hashes_per_step": 1 << args.bn, "proof_elements": 1006 * args.bn + 183,
-        "parallelism": "single GPU" if world == 1 else "batch sharded on low address bits over %d GPUs, NCCL all-gather of the round polynomials" % world,
+        "parallelism": "single GPU, %d proofs in flight" % P if world == 1 else "batch sharded on low address bits over %d GPUs, NCCL all-gather of the round polynomials, %d proofs in flight" % (world, P),
         "l2": "inputs larger than L2: 93 layer tables of %d MiB each per proof" % ((32 << args.bn) >> 20),
         "seeds": [args.seed, args.seed + 1, args.seed + 2],
     }
@@ -152,6 +158,7 @@ def main():
     ap.add_argument("--cpu-bn", type=int, default=18, help="batch of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0x6B6B72)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=0, help="proofs in flight per GPU (0 = auto: 2 on one GPU, 1 when sharded)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -193,14 +200,20 @@ def main():
         return float(t.item())
 
     n, bn = 1 << args.bn, args.bn
-    stream = torch.cuda.Stream()  # the library launches on this stream; the CUDA events below are recorded on it
-    torch.cuda.set_stream(stream)
-    ctx = gkrb200.Context(device=local_rank, max_bn=bn, stream=stream.cuda_stream)
+    # P proofs in flight: each has its own context (arena + stream) and its own host thread, so the serial host
+    # transcript of one proof (MiMC challenges, ~130 ms per 2^22 proof) overlaps the device rounds of another.
+    P = args.inflight if args.inflight > 0 else (3 if world == 1 else 2)
+    main_stream = torch.cuda.Stream()
+    streams = [torch.cuda.Stream() for _ in range(P)]  # the library launches on these; events are recorded on main_stream after joining them
+    torch.cuda.set_stream(main_stream)
+    ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream) for st_ in streams]
+    ctx = ctxs[0]
     if world > 1:
-        uid = [gkrb200.Context.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(rank, world, uid[0])
-    circuit = gkrb200.MimcCircuit(ctx)
+        for c in ctxs:  # one communicator per pipeline, created in the same order on every rank
+            uid = [gkrb200.Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            c.comm_init(rank, world, uid[0])
+    circuits = [gkrb200.MimcCircuit(c) for c in ctxs]
 
     # synthetic inputs: pinned host copies (e2e path) and device-resident copies (kernel path)
     key_np, msg_np, q_np = synth_inputs(n, args.seed), synth_inputs(n, args.seed + 1), synth_inputs(bn, args.seed + 2)
@@ -210,46 +223,78 @@ def main():
     key_hn, msg_hn = key_h.numpy().view(np.uint64), msg_h.numpy().view(np.uint64)
     torch.cuda.synchronize()
 
-    def step_resident():
-        a = circuit.AssignDevice(key_d.data_ptr(), msg_d.data_ptr(), n)
-        return gkrb200.gkr.Prove(circuit, a, q_np)
+    def step_resident(i=0):
+        a = circuits[i].AssignDevice(key_d.data_ptr(), msg_d.data_ptr(), n)
+        return gkrb200.gkr.Prove(circuits[i], a, q_np)
 
-    def step_e2e():
-        a = circuit.Assign(key_hn, msg_hn)
-        return gkrb200.gkr.Prove(circuit, a, q_np)
+    def step_e2e(i=0):
+        a = circuits[i].Assign(key_hn, msg_hn)
+        return gkrb200.gkr.Prove(circuits[i], a, q_np)
 
-    def timed(fn, steps):
+    def timed(fn, steps, workers):
+        """exactly `steps` proofs, spread over `workers` concurrent pipelines; device time between two events on main_stream"""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record(stream)
-        for _ in range(steps):
-            out = fn()
-        ev1.record(stream)
-        barrier()
-        return max_over_ranks(ev0.elapsed_time(ev1)), out
+        counts = [steps // workers + (1 if i < steps % workers else 0) for i in range(workers)]
+        outs, errs = [None] * workers, []
 
-    for _ in range(args.warmup):
-        proof = step_resident()
+        def work(i):
+            try:
+                torch.cuda.set_device(local_rank)
+                for _ in range(counts[i]):
+                    outs[i] = fn(i)
+            except Exception as e:  # surfaced after the join
+                errs.append(e)
+
+        barrier()
+        ev0.record(main_stream)
+        if workers == 1:
+            work(0)
+        else:
+            ths = [threading.Thread(target=work, args=(i,)) for i in range(workers)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        if errs:
+            raise errs[0]
+        for st_ in streams:
+            main_stream.wait_stream(st_)
+        ev1.record(main_stream)
+        barrier()
+        return max_over_ranks(ev0.elapsed_time(ev1)), [o for o in outs if o is not None]
+
+    for i in range(P):
+        for _ in range(args.warmup):
+            proof = step_resident(i)
     ref_vec = proof.to_vec().copy()
 
+    # latency of one proof alone (one pipeline), then the timed throughput run with P in flight
+    ms_lat, _ = timed(step_resident, 2, 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ctx.stats_reset()
-    ms_total, proof = timed(step_resident, args.steps)
-    st = ctx.stats()
+    for c in ctxs:
+        c.stats_reset()
+    ms_total, proofs = timed(step_resident, args.steps, P)
+    sts = [c.stats() for c in ctxs]
+    st = sts[0]
     clocks = sampler.stop() if rank == 0 else None
-    launches = sum_over_ranks(float(st.launches_total))
-    assert np.array_equal(proof.to_vec(), ref_vec), "non-deterministic proof"
+    launches = sum_over_ranks(float(sum(x.launches_total for x in sts)))
+    for pr in proofs:
+        assert np.array_equal(pr.to_vec(), ref_vec), "non-deterministic proof"
 
     # e2e through the host-buffer API
-    step_e2e()
-    ctx.stats_reset()
-    ms_e2e, proof_e = timed(step_e2e, args.steps)
-    st_e = ctx.stats()
-    assert np.array_equal(proof_e.to_vec(), ref_vec), "host-buffer path and device-resident path disagree"
-    h2d = sum_over_ranks(float(st_e.h2d_bytes)) / args.steps
-    d2h = sum_over_ranks(float(st_e.d2h_bytes)) / args.steps
+    for i in range(P):
+        step_e2e(i)
+    for c in ctxs:
+        c.stats_reset()
+    ms_e2e, proofs_e = timed(step_e2e, args.steps, P)
+    sts_e = [c.stats() for c in ctxs]
+    for pr in proofs_e:
+        assert np.array_equal(pr.to_vec(), ref_vec), "host-buffer path and device-resident path disagree"
+    h2d = sum_over_ranks(float(sum(x.h2d_bytes for x in sts_e))) / args.steps
+    d2h = sum_over_ranks(float(sum(x.d2h_bytes for x in sts_e))) / args.steps
+    circuit = circuits[0]
 
     # roofline pass: one extra step with CUDA events around every kernel launch (on the launching stream)
     ctx.set_profiling(True)
@@ -267,15 +312,15 @@ def main():
     k_ms = sp.kernel_ms[2]
     k_launches = max(int(sp.launches[2]), 1)
     achieved_gbs = sp.bytes_round / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    imad_rate, _ = ctx.microbench(0, 2000)       # G IMAD.WIDE.U32 / s, measured live
+    imad_rate = max(ctx.microbench(0, 2000)[0], ctx.microbench(2, 2000)[0])  # G IMAD.WIDE.U32 / s (independent and carry-chained forms), measured live
     frmul_rate, _ = ctx.microbench(1, 1000)      # G Fr-mul/s of the library's own multiplier at full occupancy
-    int_peak = imad_rate / 136.0                 # 136 wide MACs per Montgomery product
+    int_peak = max(imad_rate / 136.0, frmul_rate)  # 136 wide MACs per Montgomery product; the multiplier itself sustains the pipe best
     achieved_mul = sp.fr_mul_round / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_round (fold + round evaluation; K3+K4)", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src, "launches": k_launches,
+    roofline = {"bound": "hbm", "kernel": "k_round_cf (fold + factored round evaluation; K3+K4)", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC.get(args.bn), "traffic_note": NCU_TRAFFIC_NOTE, "peak_source": peak_src, "launches": k_launches,
                 "avg_launch_us": k_ms * 1e3 / k_launches, "algorithmic_bytes_per_launch": sp.bytes_round / k_launches,
-                "note": "k_round is integer-pipe bound (45-51 Fr-mul per 192-576 B), not HBM bound: see roofline_int"}
-    roofline_int = {"bound": "integer multiply pipe (IMAD.WIDE.U32, fmaheavy)", "achieved": achieved_mul, "peak": int_peak, "unit": "G Fr-mul/s",
+                "note": "k_round_cf is integer-pipe bound (19-23 Fr-mul per 128-384 B), not HBM bound: see roofline_int"}
+    roofline_int = {"bound": "integer multiply pipe (IMAD.WIDE.U32 on fmaheavy: 32x32->64 multiply-add, half the 32-bit IMAD rate)", "achieved": achieved_mul, "peak": int_peak, "unit": "G Fr-mul/s",
                     "frac": achieved_mul / int_peak if int_peak else None, "imad_wide_gmacs_measured": imad_rate, "macs_per_fr_mul": 136,
                     "fr_mul_microbench_gmuls": frmul_rate, "frac_of_fr_mul_microbench": achieved_mul / frmul_rate if frmul_rate else None,
                     "share_of_step_kernel_time": k_ms / max(sum(sp.kernel_ms), 1e-9)}
@@ -294,17 +339,20 @@ def main():
         line = {
             "metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr, Montgomery)",
-            "data": "synthetic", "config": workload_config(args, world), "clocks": clocks,
+            "data": "synthetic", "config": workload_config(args, world, P), "clocks": clocks,
             "e2e": {"value": n / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_int": roofline_int, "kernels_profile_step": kernels,
-            "breakdown_ms_per_step": {"transcript_host": st.transcript_ms / args.steps, "wait_device": st.wait_ms / args.steps,
-                                      "comm_host": st.comm_ms / args.steps, "rounds": int(st.rounds // args.steps)},
+            "pipeline": {"proofs_in_flight": P, "latency_ms_one_proof_alone": ms_lat / 2,
+                         "note": "value/e2e time K proofs with P in flight (own context, stream and host thread each): the serial host transcript of one overlaps the device rounds of another"},
+            "breakdown_ms_per_proof_pipeline0": {"transcript_host": st.transcript_ms / max(1, (args.steps + P - 1) // P), "wait_device": st.wait_ms / max(1, (args.steps + P - 1) // P),
+                                      "comm_host": st.comm_ms / max(1, (args.steps + P - 1) // P), "rounds": int(st.rounds // max(1, (args.steps + P - 1) // P))},
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
+    for c in ctxs:
+        c.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0

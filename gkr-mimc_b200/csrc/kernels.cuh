@@ -785,28 +785,24 @@ __global__ void __launch_bounds__(256) k_fr_batch(int op, const FrRaw* __restric
 // ------------------------------------------------------------------------------------------------
 // Integer-pipe microbenchmarks (roofline denominators)
 // ------------------------------------------------------------------------------------------------
-// kind 0: 8 independent IMAD.WIDE.U32 accumulation chains per thread
+// kind 0: 8 IMAD.WIDE.U32 accumulation chains per thread.  Every multiply takes one operand from the NEIGHBOUR chain's
+// previous value, so no product is loop-invariant: an earlier version multiplied the same x*y every iteration and ptxas
+// strength-reduced the whole loop to IADD3 (it reported 18.5 T "MAC"/s that were additions).  Honest rate on B200:
+// ~7-9 T/s (a 32x32->64 multiply-add issues at half the 32-bit IMAD rate).
 __global__ void __launch_bounds__(256) k_bench_imad_wide(uint64_t* out, int iters, uint32_t seed) {
-    uint32_t x = seed + threadIdx.x, y = seed * 3u + blockIdx.x;
-    uint64_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+    uint64_t c[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) c[i] = (uint64_t)seed * (i + 1) + threadIdx.x;
+    const uint32_t y = seed | 1u;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            asm volatile(
-                "mad.wide.u32 %0, %8, %9, %0;\n\t"
-                "mad.wide.u32 %1, %8, %9, %1;\n\t"
-                "mad.wide.u32 %2, %8, %9, %2;\n\t"
-                "mad.wide.u32 %3, %8, %9, %3;\n\t"
-                "mad.wide.u32 %4, %8, %9, %4;\n\t"
-                "mad.wide.u32 %5, %8, %9, %5;\n\t"
-                "mad.wide.u32 %6, %8, %9, %6;\n\t"
-                "mad.wide.u32 %7, %8, %9, %7;"
-                : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
-                : "r"(x), "r"(y));
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c[k]) : "r"((uint32_t)c[(k + 1) & 7]), "r"(y));
         }
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
 }
 // kind 1: two independent dependent-chains of fr_mul per thread (what the prover kernels look like)
 __global__ void k_bench_fr_mul(FrRaw* out, int iters, uint32_t seed) {
