@@ -26,6 +26,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "gkr-mimc_b200"))
 
+_JSON_OUT = sys.stdout
 METRIC = "proven MiMC hashes/sec (bit-exact GKR proof)"
 UNIT = "hashes/s"
 Q3 = 0x30644E72E131A029  # top limb of q: any element with top limb < Q3 is canonical
@@ -127,7 +128,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     return 0
 
 
@@ -164,6 +165,11 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) go to stderr instead
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
@@ -350,7 +356,7 @@ def main():
                                       "comm_host": st.comm_ms / max(1, (args.steps + P - 1) // P), "rounds": int(st.rounds // max(1, (args.steps + P - 1) // P))},
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     for c in ctxs:
         c.close()
     if dist is not None:

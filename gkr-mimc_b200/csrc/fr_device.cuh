@@ -255,6 +255,38 @@ __device__ __forceinline__ Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
 __device__ __noinline__ Fr fr_mulc(const Fr a, const Fr b) { return fr_mul(a, b); }
 __device__ __forceinline__ Fr fr_sqrc(const Fr& a) { return fr_mulc(a, a); }
 
+// acc (17 x 32-bit limbs, one every `stride` words) += a*b as a PLAIN 512-bit product: no Montgomery reduction.
+// Half the multiplier work of fr_mul (64 of its 136 wide multiply-adds); whoever consumes the sum reduces it once
+// (the host, for the round sums: REDC(sum of products) == sum of Montgomery products, exactly).  544 bits hold
+// 2^36 products of values < q.  Out of line for the same reason as fr_mulc.
+__device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr a, const Fr b) {
+    uint32_t P[18], Qd[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) P[i] = 0, Qd[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t* S = (i & 1) ? Qd : P;
+        uint32_t* T = (i & 1) ? P : Qd;
+        const uint32_t bi = b.v[i];
+        chain4(S[i], S[i + 1], S[i + 2], S[i + 3], S[i + 4], S[i + 5], S[i + 6], S[i + 7], S[i + 8], a.v[0], a.v[2], a.v[4], a.v[6], bi);
+        chain4(T[i + 1], T[i + 2], T[i + 3], T[i + 4], T[i + 5], T[i + 6], T[i + 7], T[i + 8], T[i + 9], a.v[1], a.v[3], a.v[5], a.v[7], bi);
+    }
+    // product = P + Qd (< 2^512: limb 16 of the sum is zero); carries ride the condition code from one statement to the
+    // next (nothing between them touches it -- the usual multi-precision idiom)
+    uint32_t w[17];
+#pragma unroll
+    for (int l = 0; l < 17; l++) w[l] = acc[l * stride];
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(P[0]) : "r"(Qd[0]));
+#pragma unroll
+    for (int l = 1; l < 16; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(P[l]) : "r"(Qd[l]));
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(w[0]) : "r"(P[0]));
+#pragma unroll
+    for (int l = 1; l < 16; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(w[l]) : "r"(P[l]));
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(w[16]));
+#pragma unroll
+    for (int l = 0; l < 17; l++) acc[l * stride] = w[l];
+}
+
 // x^7 = ((x^2 * x)^2) * x  -- same chain as hash/poseidon.go:129-135 and circuit/gates/cipher.go:37-40
 __device__ __forceinline__ Fr fr_pow7(const Fr& x) {
     Fr t = fr_sqr(x);

@@ -112,14 +112,14 @@ struct gkrb200_ctx {
     FrRaw* d_mults = nullptr;    // [MAX_CLAIMS]
     FrRaw* partials = nullptr;   // [max_grid][MAX_EV]
     unsigned int* ticket = nullptr;
-    FrRaw* d_local = nullptr;    // [32] this rank's contribution (multi-GPU); [16..19) residual entries of the last fold
-    FrRaw* d_all = nullptr;      // [8*32]
+    FrRaw* d_local = nullptr;    // [64] this rank's contribution (multi-GPU); [16..19) residual entries of the last fold
+    FrRaw* d_all = nullptr;      // [8*64]
     FrRaw* d_resid = nullptr;    // [3][TAIL_MAX] residual tables after the last device fold
-    uint32_t* partials_w = nullptr;  // [max_grid][8][9] per-block 288-bit sums of the factored cipher round
+    uint32_t* partials_w = nullptr;  // [max_grid][8][17] per-block 288-bit sums of the factored cipher round
     int max_grid = 0;
 
     // pinned, device-mapped result slot
-    FrRaw* h_result = nullptr;  // [256] (8 KiB: 8 ranks x 8 wide sums x 9 tagged 64-bit words fit)
+    FrRaw* h_result = nullptr;  // [512] (16 KiB: 8 ranks x 8 wide sums x 17 tagged 64-bit words fit)
     volatile uint32_t* h_flag = nullptr;
     uint32_t seq = 0;
     H::Fr* h_stage = nullptr;  // pinned staging for qprimes/mults uploads [MAX_CLAIMS*(max_bn+1)]
@@ -165,7 +165,7 @@ struct gkrb200_ctx {
     size_t par8_max_pairs = 8192;  // rounds with at most this many pairs spread one pair over 8 lanes
     bool force_generic = false;  // test hook: run cipher layers through the generic evaluate-at-9-points kernel
     int exchange_and_fetch(int nacc, H::Fr* out);
-    int exchange_and_fetch_wide(int nm, H::Fr* out);
+    int exchange_and_fetch_wide(int nm, int wl, H::Fr* out);
     int fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX_FWD]);
     int tail_len = TAIL_MAX_FWD;     // option: residual length (entries over all ranks) handed to the host
     int sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn_total, const H::Fr* q, const H::Fr* trusted_claim, const H::Fr& ark, bool use_shards,
@@ -277,48 +277,67 @@ static inline int grid_for(size_t work_items, int block, int max_grid) {
 
 // ------------------------------------------------------------------------------------------------ factored cipher round: launch plumbing
 static constexpr int CF_BLOCK = 128;
-static constexpr int CF_MINB = 4;
+static constexpr int CF_MINB1 = 3;  // PAR == 1: 7-8 accumulators x 17 limbs x 128 threads = 61-70 KB of shared memory per block
+static constexpr int CF_MINB8 = 4;
+static constexpr int CF_WL1 = 17;   // limbs per accumulator, PAR == 1 (plain 512-bit products summed)
+static constexpr int CF_WL8 = 9;    // PAR == 8 (reduced products summed)
 static constexpr size_t CF_SMEM_PAR8 = (8 * 9 + (CF_BLOCK / 32) * 8 * 9 + (CF_BLOCK / 8) * 8 * 9) * 4;
+static inline size_t cf_smem(int nm, bool par8) { return par8 ? CF_SMEM_PAR8 : (size_t)nm * CF_WL1 * CF_BLOCK * 4; }
 
 typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
 static cf_kernel_t cf_kernel(bool fold, int nm, bool par8) {
     using namespace gkr;
-#define CF_K(F, N, P) k_round_cf<F, N, P, CF_BLOCK, CF_MINB>
-    static const cf_kernel_t tab[2][2][2] = {{{CF_K(false, 7, 1), CF_K(false, 7, 8)}, {CF_K(false, 8, 1), CF_K(false, 8, 8)}},
-                                             {{CF_K(true, 7, 1), CF_K(true, 7, 8)}, {CF_K(true, 8, 1), CF_K(true, 8, 8)}}};
-#undef CF_K
+#define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK, CF_MINB1>
+#define CF_K8(F, N) k_round_cf<F, N, 8, CF_BLOCK, CF_MINB8>
+    static const cf_kernel_t tab[2][2][2] = {{{CF_K1(false, 7), CF_K8(false, 7)}, {CF_K1(false, 8), CF_K8(false, 8)}},
+                                             {{CF_K1(true, 7), CF_K8(true, 7)}, {CF_K1(true, 8), CF_K8(true, 8)}}};
+#undef CF_K1
+#undef CF_K8
     return tab[fold ? 1 : 0][nm == 8 ? 1 : 0][par8 ? 1 : 0];
 }
 static int set_cf_attrs() {
     for (int f = 0; f < 2; f++)
         for (int n = 7; n <= 8; n++)
             for (int p = 0; p < 2; p++)
-                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, p), cudaFuncAttributeMaxDynamicSharedMemorySize, n * 9 * CF_BLOCK * 4));
+                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem(n, p)));
     return 0;
 }
 
-// 288-bit plain sums (one per rank; tagged 64-bit words, limb in the low half) -> canonical field element
-static H::Fr wide_to_fr(const volatile uint64_t* w, int n_ranks, size_t rank_stride_words) {
-    uint64_t acc[10] = {0};
+// x (< 2^256, any) mod q
+static H::Fr reduce_256(H::Fr x) {
+    for (;;) {
+        H::ull s0, s1, s2, s3;
+        unsigned char b = _subborrow_u64(0, x.l[0], H::Q[0], &s0);
+        b = _subborrow_u64(b, x.l[1], H::Q[1], &s1);
+        b = _subborrow_u64(b, x.l[2], H::Q[2], &s2);
+        b = _subborrow_u64(b, x.l[3], H::Q[3], &s3);
+        if (b) return x;
+        x = H::Fr{{s0, s1, s2, s3}};
+    }
+}
+// Device sums (one per rank; tagged 64-bit words with the 32-bit limb in the low half) -> canonical field element.
+//   wl == 9 : 288-bit sum of canonical Montgomery values       -> value mod q
+//   wl == 17: 544-bit sum of PLAIN products x*y of Montgomery values -> REDC(sum) = sum * 2^-256 mod q, which is exactly the
+//             sum of the Montgomery products fr.Mul would have produced one by one.
+static H::Fr wide_to_fr(const volatile uint64_t* w, int wl, int n_ranks, size_t rank_stride_words) {
+    uint64_t acc[20] = {0};
     for (int g = 0; g < n_ranks; g++)
-        for (int l = 0; l < 9; l++) acc[l] += (uint32_t)w[(size_t)g * rank_stride_words + l];
-    for (int l = 0; l < 9; l++) {  // carry-normalise to 32-bit limbs
+        for (int l = 0; l < wl; l++) acc[l] += (uint32_t)w[(size_t)g * rank_stride_words + l];
+    for (int l = 0; l < wl + 1; l++) {  // carry-normalise to 32-bit limbs
         acc[l + 1] += acc[l] >> 32;
         acc[l] &= 0xffffffffu;
     }
-    H::Fr lo{{acc[0] | (acc[1] << 32), acc[2] | (acc[3] << 32), acc[4] | (acc[5] << 32), acc[6] | (acc[7] << 32)}};
-    const uint64_t hi = acc[8] | (acc[9] << 32);  // < 2^36
-    for (;;) {  // lo < 2^256 < 6q
-        H::ull s0, s1, s2, s3;
-        unsigned char b = _subborrow_u64(0, lo.l[0], H::Q[0], &s0);
-        b = _subborrow_u64(b, lo.l[1], H::Q[1], &s1);
-        b = _subborrow_u64(b, lo.l[2], H::Q[2], &s2);
-        b = _subborrow_u64(b, lo.l[3], H::Q[3], &s3);
-        if (b) break;
-        lo = H::Fr{{s0, s1, s2, s3}};
+    const H::Fr R2{{H::R2[0], H::R2[1], H::R2[2], H::R2[3]}};
+    auto limb64 = [&](int i) { return acc[2 * i] | (acc[2 * i + 1] << 32); };
+    const H::Fr lo = reduce_256(H::Fr{{limb64(0), limb64(1), limb64(2), limb64(3)}});
+    if (wl == 9) {
+        const uint64_t hi = limb64(4);  // < 2^36
+        return H::add(lo, H::mul(H::Fr{{hi, 0, 0, 0}}, R2));  // hi * 2^256 mod q = mont(hi, R^2)
     }
-    // hi * 2^256 mod q = mont(hi, R^2)
-    return H::add(lo, H::mul(H::Fr{{hi, 0, 0, 0}}, H::Fr{{H::R2[0], H::R2[1], H::R2[2], H::R2[3]}}));
+    const H::Fr mid = reduce_256(H::Fr{{limb64(4), limb64(5), limb64(6), limb64(7)}});
+    const uint64_t top = limb64(8);  // < 2^36
+    // sum = lo + 2^256 * (mid + 2^256 * top)  =>  sum * 2^-256 = lo * 2^-256 + mid + top * 2^256
+    return H::add(H::add(H::mul(lo, H::Fr{{1, 0, 0, 0}}), mid), H::mul(H::Fr{{top, 0, 0, 0}}, R2));
 }
 
 // ------------------------------------------------------------------------------------------------ init / free
@@ -352,7 +371,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     const int nsmall = (max_bn + 1) / 2;
     const size_t small = (size_t)1 << nsmall;
     size_t total = 93 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
-                   (size_t)c->max_grid * MAX_EV + 32 + 8 * 32 + 3 * 32 + 64 + ((size_t)c->max_grid * 8 * 9 * 4 + 31) / 32;
+                   (size_t)c->max_grid * MAX_EV + 64 + 8 * 64 + 3 * 32 + 64 + ((size_t)c->max_grid * 8 * 17 * 4 + 31) / 32;
     cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
     if (me != cudaSuccess) {
         delete c;
@@ -367,15 +386,15 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     c->d_q = p; p += (size_t)MAX_CLAIMS * (max_bn + 1);
     c->d_mults = p; p += MAX_CLAIMS;
     c->partials = p; p += (size_t)c->max_grid * MAX_EV;
-    c->d_local = p; p += 32;
-    c->d_all = p; p += 8 * 32;
+    c->d_local = p; p += 64;
+    c->d_all = p; p += 8 * 64;
     c->d_resid = p; p += 3 * 32;
-    c->partials_w = (uint32_t*)p; p += ((size_t)c->max_grid * 8 * 9 * 4 + 31) / 32;
+    c->partials_w = (uint32_t*)p; p += ((size_t)c->max_grid * 8 * 17 * 4 + 31) / 32;
     CUDA_TRY(cudaMalloc(&c->ticket, 64));
     CUDA_TRY(cudaMemset(c->ticket, 0, 64));
-    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 256 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
-    memset(c->h_result, 0, 256 * sizeof(FrRaw) + 64);
-    c->h_flag = (volatile uint32_t*)(c->h_result + 256);
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 512 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
+    memset(c->h_result, 0, 512 * sizeof(FrRaw) + 64);
+    c->h_flag = (volatile uint32_t*)(c->h_result + 512);
     *c->h_flag = 0;
     CUDA_TRY(cudaHostAlloc((void**)&c->h_stage, (size_t)MAX_CLAIMS * (max_bn + 2) * sizeof(H::Fr), cudaHostAllocDefault));
     // opt in to the dynamic shared memory the round kernels need
@@ -782,9 +801,9 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
 }
 
 // Wide variant for the factored cipher round: nm 288-bit sums per rank.
-int gkrb200_ctx::exchange_and_fetch_wide(int nm, H::Fr* out) {
+int gkrb200_ctx::exchange_and_fetch_wide(int nm, int wl, H::Fr* out) {
     const int W = eff_world();
-    const size_t words = (size_t)nm * 9;
+    const size_t words = (size_t)nm * wl;
     if (W > 1) {
         const double t0 = now_ms();
         NCCL_TRY(g_nccl.AllGather(d_local, d_all, words * 8, ncclUint8, comm, stream));
@@ -795,7 +814,7 @@ int gkrb200_ctx::exchange_and_fetch_wide(int nm, H::Fr* out) {
     }
     TRY(wait_words(seq, words * (size_t)W));
     const volatile uint64_t* w = (const volatile uint64_t*)h_result;
-    for (int i = 0; i < nm; i++) out[i] = wide_to_fr(w + (size_t)i * 9, W, words);
+    for (int i = 0; i < nm; i++) out[i] = wide_to_fr(w + (size_t)i * wl, wl, W, words);
     st.d2h_bytes += words * 8 * (size_t)W;
     return 0;
 }
@@ -896,8 +915,8 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         a.red.ticket = ticket;
         a.red.result = W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result;
         a.red.seq = seq;
-        const int grid = grid_for(par8 ? half * 8 : half, CF_BLOCK, n_sm * CF_MINB);  // at most one resident wave
-        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, CF_BLOCK, par8 ? CF_SMEM_PAR8 : (size_t)nm * 9 * CF_BLOCK * 4, a);
+        const int grid = grid_for(par8 ? half * 8 : half, CF_BLOCK, n_sm * (par8 ? CF_MINB8 : CF_MINB1));  // at most one resident wave
+        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, CF_BLOCK, cf_smem(nm, par8), a);
         CUDA_TRY(cudaGetLastError());
         st.fr_mul_round += (uint64_t)half * ((nm == 8 ? 20 : 18) + (mk > c ? 1 : 0) + (do_fold ? 4 : 0));
         st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
@@ -905,7 +924,7 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
             cur[0] = dstp[0];
             cur[1] = dstp[1];
         }
-        TRY(exchange_and_fetch_wide(nm, m));
+        TRY(exchange_and_fetch_wide(nm, par8 ? CF_WL8 : CF_WL1, m));
         const double t0 = now_ms();
         const H::Fr w0 = H::sub(one, q[k]), w1 = H::sub(q[k], w0);  // eq(q_k, t) = w0 + w1*t
         if (nm == 7) {

@@ -421,8 +421,32 @@ __device__ long long g_trace[16];
 #define GKR_T(i) do { } while (0)
 #endif
 
+// sm[(k*WL + l)*BLOCK + i] += sm[(k*WL + l)*BLOCK + i + stride]  as WL-limb integers
+template <int WL, int BLOCK>
+__device__ __forceinline__ void widen_pair_add(uint32_t* sm, int k, int i, int stride) {
+    uint32_t a[WL], b[WL];
+#pragma unroll
+    for (int l = 0; l < WL; l++) {
+        a[l] = sm[(k * WL + l) * BLOCK + i];
+        b[l] = sm[(k * WL + l) * BLOCK + i + stride];
+    }
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a[0]) : "r"(b[0]));
+#pragma unroll
+    for (int l = 1; l < WL - 1; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(a[l]) : "r"(b[l]));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[WL - 1]) : "r"(b[WL - 1]));
+#pragma unroll
+    for (int l = 0; l < WL; l++) sm[(k * WL + l) * BLOCK + i] = a[l];
+}
+template <int WL>
+__device__ __forceinline__ void widen_add(uint32_t (&a)[WL], const uint32_t (&b)[WL]) {
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a[0]) : "r"(b[0]));
+#pragma unroll
+    for (int l = 1; l < WL - 1; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(a[l]) : "r"(b[l]));
+    asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[WL - 1]) : "r"(b[WL - 1]));
+}
+
 struct WideOut {
-    uint32_t* partials;            // [gridDim.x][NM][9] device scratch
+    uint32_t* partials;            // [gridDim.x][NM][WL] device scratch
     unsigned int* ticket;          // device counter, zero between launches
     unsigned long long* result;    // NM x 9 words, each (seq << 32) | limb of a 288-bit plain sum (NOT reduced mod q);
                                    // device memory or mapped host memory
@@ -456,17 +480,17 @@ __device__ __forceinline__ void publish_word(unsigned long long* dst, uint32_t s
 // Grid stage shared by both layouts of k_round_cf.  tot: this block's NM x 9 limb sums in shared memory
 // (tot[k*9 + l]); scratch: >= (BLOCK/8) * NM * 9 words of shared memory.  No field multiplication anywhere:
 // the host reduces the NM wide sums modulo q.
-template <int NM, int BLOCK>
+template <int NM, int WL, int BLOCK>
 __device__ __forceinline__ void grid_stage_wide(const uint32_t* tot, uint32_t* scratch, const WideOut& out) {
     const int tid = threadIdx.x;
     __shared__ bool is_last_r;
     GKR_T(5);
     if (gridDim.x == 1) {
-        if (tid < NM * 9) publish_word(out.result + tid, out.seq, tot[tid]);
+        for (int i = tid; i < NM * WL; i += BLOCK) publish_word(out.result + i, out.seq, tot[i]);
         GKR_T(6);
         return;
     }
-    if (tid < NM * 9) out.partials[(size_t)blockIdx.x * (NM * 9) + tid] = tot[tid];
+    for (int i = tid; i < NM * WL; i += BLOCK) out.partials[(size_t)blockIdx.x * (NM * WL) + i] = tot[i];
     __threadfence();
     __syncthreads();
     if (tid == 0) is_last_r = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
@@ -476,43 +500,43 @@ __device__ __forceinline__ void grid_stage_wide(const uint32_t* tot, uint32_t* s
     // last block: lane group (tid >> 3) sums the partials of blocks tid>>3, +BLOCK/8, ... for accumulator tid & 7
     {
         const int k = tid & 7, slice = tid >> 3;
-        uint32_t a[9];
+        uint32_t a[WL];
 #pragma unroll
-        for (int l = 0; l < 9; l++) a[l] = 0;
+        for (int l = 0; l < WL; l++) a[l] = 0;
         if (k < NM) {
 #pragma unroll 1
             for (unsigned b = slice; b < gridDim.x; b += BLOCK / 8) {
-                const uint32_t* pp = out.partials + (size_t)b * (NM * 9) + k * 9;
-                uint32_t w[9];
+                const uint32_t* pp = out.partials + (size_t)b * (NM * WL) + k * WL;
+                uint32_t w[WL];
 #pragma unroll
-                for (int l = 0; l < 9; l++) w[l] = __ldcg(pp + l);
-                wide9_add(a, w);
+                for (int l = 0; l < WL; l++) w[l] = __ldcg(pp + l);
+                widen_add<WL>(a, w);
             }
 #pragma unroll
-            for (int l = 0; l < 9; l++) scratch[(slice * NM + k) * 9 + l] = a[l];
+            for (int l = 0; l < WL; l++) scratch[(slice * NM + k) * WL + l] = a[l];
         }
     }
     __syncthreads();
     if (tid < NM) {
-        uint32_t a[9];
+        uint32_t a[WL];
 #pragma unroll
-        for (int l = 0; l < 9; l++) a[l] = scratch[tid * 9 + l];
+        for (int l = 0; l < WL; l++) a[l] = scratch[tid * WL + l];
 #pragma unroll 1
         for (int sl = 1; sl < BLOCK / 8; sl++) {
-            uint32_t w[9];
+            uint32_t w[WL];
 #pragma unroll
-            for (int l = 0; l < 9; l++) w[l] = scratch[(sl * NM + tid) * 9 + l];
-            wide9_add(a, w);
+            for (int l = 0; l < WL; l++) w[l] = scratch[(sl * NM + tid) * WL + l];
+            widen_add<WL>(a, w);
         }
 #pragma unroll
-        for (int l = 0; l < 9; l++) publish_word(out.result + tid * 9 + l, out.seq, a[l]);
+        for (int l = 0; l < WL; l++) publish_word(out.result + tid * WL + l, out.seq, a[l]);
     }
     if (tid == 0) *out.ticket = 0;
     GKR_T(6);
 }
 
-// PAR = 1 layout: per-thread 288-bit accumulators in shared memory (sm[(k*9+l)*BLOCK + tid]) -> block tree -> grid stage
-template <int NM, int BLOCK>
+// PAR = 1 layout: per-thread WL-limb accumulators in shared memory (sm[(k*WL+l)*BLOCK + tid]) -> block tree -> grid stage
+template <int NM, int WL, int BLOCK>
 __device__ __forceinline__ void grid_reduce_wide_raw(uint32_t* sm, const WideOut& out) {
     const int tid = threadIdx.x;
     __syncthreads();
@@ -523,17 +547,25 @@ __device__ __forceinline__ void grid_reduce_wide_raw(uint32_t* sm, const WideOut
 #pragma unroll 1
         for (int it = tid; it < items; it += BLOCK) {
             const int k = it / stride, i = it - k * stride;
-            wide_pair_add<BLOCK>(sm, k, i, stride);
+            widen_pair_add<WL, BLOCK>(sm, k, i, stride);
         }
         __syncthreads();
     }
     // compact the block totals (column 0 of every row) to the front, then reuse the rest as scratch
-    uint32_t v = 0;
-    if (tid < NM * 9) v = sm[tid * BLOCK];
+    uint32_t v[(NM * WL + BLOCK - 1) / BLOCK];
+#pragma unroll
+    for (int j = 0; j < (NM * WL + BLOCK - 1) / BLOCK; j++) {
+        const int i = tid + j * BLOCK;
+        v[j] = i < NM * WL ? sm[i * BLOCK] : 0;
+    }
     __syncthreads();
-    if (tid < NM * 9) sm[tid] = v;
+#pragma unroll
+    for (int j = 0; j < (NM * WL + BLOCK - 1) / BLOCK; j++) {
+        const int i = tid + j * BLOCK;
+        if (i < NM * WL) sm[i] = v[j];
+    }
     __syncthreads();
-    grid_stage_wide<NM, BLOCK>(sm, sm + NM * 9, out);
+    grid_stage_wide<NM, WL, BLOCK>(sm, sm + NM * WL, out);
 }
 
 // Suffix eq tables of one layer's challenge vector q[0..n): block 0 builds the stages of the low part
@@ -594,12 +626,13 @@ template <bool FOLD, int NM, int PAR, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
     static_assert(NM == 7 || NM == 8, "7 coefficient sums (m_7 from the claim) or all 8");
     static_assert(PAR == 1 || PAR == 8, "one thread or eight lanes per pair");
-    extern __shared__ uint32_t sm[];  // NM * 9 * BLOCK words
+    extern __shared__ uint32_t sm[];  // PAR == 1: NM * 17 * BLOCK words; PAR == 8: see CF_SMEM_PAR8
     const int tid = threadIdx.x;
     GKR_T(0);
+    constexpr int WL1 = 17;  // limbs of a PAR == 1 accumulator (sum of plain 512-bit products)
     if (PAR == 1) {
 #pragma unroll 1
-        for (int i = tid; i < NM * 9 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
+        for (int i = tid; i < NM * WL1 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
     }
     GKR_T(1);
     const Fr r = fr_unpack(a.r);
@@ -626,14 +659,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
             bp[4] = fr_sqrc(bp[2]);
             bp[5] = fr_mulc(bp[4], bv);
             bp[6] = fr_sqrc(bp[3]);
-            if (NM == 8) wide_acc_add<BLOCK>(sm + (size_t)7 * 9 * BLOCK + tid, fr_mulc(u, fr_mulc(bp[6], bv)));
+            // the NM products that only feed the sums are accumulated UNREDUCED (fr_mul_acc_wide): m_i += (T a^(7-i)) * b^i
+            if (NM == 8) fr_mul_acc_wide(sm + (size_t)7 * WL1 * BLOCK + tid, BLOCK, u, fr_mulc(bp[6], bv));
 #pragma unroll
             for (int i = 6; i >= 1; i--) {
                 u = fr_mulc(u, av);  // T * a^(7-i)
-                wide_acc_add<BLOCK>(sm + (size_t)i * 9 * BLOCK + tid, fr_mulc(u, bp[i]));
+                fr_mul_acc_wide(sm + (size_t)i * WL1 * BLOCK + tid, BLOCK, u, bp[i]);
             }
-            u = fr_mulc(u, av);
-            wide_acc_add<BLOCK>(sm + tid, u);
+            fr_mul_acc_wide(sm + tid, BLOCK, u, av);  // m_0 += (T a^6) * a
         }
     } else {
         const int j = tid & 7;
@@ -726,10 +759,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
             for (int l = 0; l < 9; l++) tot[tid * 9 + l] = acc9[l];
         }
         __syncthreads();
-        grid_stage_wide<NM, BLOCK>(tot, sm + 8 * 9 + NW * 8 * 9, a.red);
+        grid_stage_wide<NM, 9, BLOCK>(tot, sm + 8 * 9 + NW * 8 * 9, a.red);
         return;
     }
-    grid_reduce_wide_raw<NM, BLOCK>(sm, a.red);
+    grid_reduce_wide_raw<NM, WL1, BLOCK>(sm, a.red);
 }
 
 // copies n tagged 64-bit words (see publish_word) to mapped host memory; the tags travel with the data
