@@ -88,6 +88,7 @@ static constexpr int ROUND_BLOCK = 128;
 static constexpr int ROUND_MINB = 5;  // resident blocks per SM the round kernels are compiled for
 static constexpr int MAX_EV = 9;
 static constexpr int TAIL_MAX_FWD = 32;
+static constexpr int CF_MINB1_FWD = 3;
 
 static inline double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -115,6 +116,7 @@ struct gkrb200_ctx {
     FrRaw* d_local = nullptr;    // [64] this rank's contribution (multi-GPU); [16..19) residual entries of the last fold
     FrRaw* d_all = nullptr;      // [8*64]
     FrRaw* d_resid = nullptr;    // [3][TAIL_MAX] residual tables after the last device fold
+    int cf_blocks_per_sm1[2] = {CF_MINB1_FWD, CF_MINB1_FWD};
     uint32_t* partials_w = nullptr;  // [max_grid][8][17] per-block 288-bit sums of the factored cipher round
     int max_grid = 0;
 
@@ -276,18 +278,19 @@ static inline int grid_for(size_t work_items, int block, int max_grid) {
 
 
 // ------------------------------------------------------------------------------------------------ factored cipher round: launch plumbing
-static constexpr int CF_BLOCK = 128;
-static constexpr int CF_MINB1 = 3;  // PAR == 1: 7-8 accumulators x 17 limbs x 128 threads = 61-70 KB of shared memory per block
+static constexpr int CF_BLOCK = 128;  // PAR == 8 kernels
+static constexpr int CF_BLOCK1 = 128; // PAR == 1 kernels: 7-8 accumulators x 17 limbs x 128 threads = 61-70 KB of shared memory per block (64-thread blocks measured 30 % slower)
+static constexpr int CF_MINB1 = 3;    // -> 3 blocks (12 warps) per SM
 static constexpr int CF_MINB8 = 4;
 static constexpr int CF_WL1 = 17;   // limbs per accumulator, PAR == 1 (plain 512-bit products summed)
 static constexpr int CF_WL8 = 9;    // PAR == 8 (reduced products summed)
 static constexpr size_t CF_SMEM_PAR8 = (8 * 9 + (CF_BLOCK / 32) * 8 * 9 + (CF_BLOCK / 8) * 8 * 9) * 4;
-static inline size_t cf_smem(int nm, bool par8) { return par8 ? CF_SMEM_PAR8 : (size_t)nm * CF_WL1 * CF_BLOCK * 4; }
+static inline size_t cf_smem(int nm, bool par8) { return par8 ? CF_SMEM_PAR8 : (size_t)nm * CF_WL1 * CF_BLOCK1 * 4; }
 
 typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
 static cf_kernel_t cf_kernel(bool fold, int nm, bool par8) {
     using namespace gkr;
-#define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK, CF_MINB1>
+#define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK1, CF_MINB1>
 #define CF_K8(F, N) k_round_cf<F, N, 8, CF_BLOCK, CF_MINB8>
     static const cf_kernel_t tab[2][2][2] = {{{CF_K1(false, 7), CF_K8(false, 7)}, {CF_K1(false, 8), CF_K8(false, 8)}},
                                              {{CF_K1(true, 7), CF_K8(true, 7)}, {CF_K1(true, 8), CF_K8(true, 8)}}};
@@ -371,7 +374,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     const int nsmall = (max_bn + 1) / 2;
     const size_t small = (size_t)1 << nsmall;
     size_t total = 93 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
-                   (size_t)c->max_grid * MAX_EV + 64 + 8 * 64 + 3 * 32 + 64 + ((size_t)c->max_grid * 8 * 17 * 4 + 31) / 32;
+                   (size_t)c->max_grid * MAX_EV + 64 + 8 * 64 + 3 * 32 + 64 + ((size_t)c->n_sm * 8 * 8 * 17 * 4 + 31) / 32;
     cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
     if (me != cudaSuccess) {
         delete c;
@@ -389,7 +392,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     c->d_local = p; p += 64;
     c->d_all = p; p += 8 * 64;
     c->d_resid = p; p += 3 * 32;
-    c->partials_w = (uint32_t*)p; p += ((size_t)c->max_grid * 8 * 17 * 4 + 31) / 32;
+    c->partials_w = (uint32_t*)p; p += ((size_t)c->n_sm * 8 * 8 * 17 * 4 + 31) / 32;
     CUDA_TRY(cudaMalloc(&c->ticket, 64));
     CUDA_TRY(cudaMemset(c->ticket, 0, 64));
     CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 512 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
@@ -404,6 +407,11 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
     TRY(set_cf_attrs());
+    for (int n = 7; n <= 8; n++) {  // resident blocks per SM of the PAR == 1 kernels (shared-memory bound): the grid is exactly one wave
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cf_kernel(true, n, false), CF_BLOCK1, cf_smem(n, false)));
+        c->cf_blocks_per_sm1[n - 7] = nb > 0 ? nb : 1;
+    }
     *out = c;
     return 0;
 }
@@ -915,8 +923,9 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         a.red.ticket = ticket;
         a.red.result = W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result;
         a.red.seq = seq;
-        const int grid = grid_for(par8 ? half * 8 : half, CF_BLOCK, n_sm * (par8 ? CF_MINB8 : CF_MINB1));  // at most one resident wave
-        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, CF_BLOCK, cf_smem(nm, par8), a);
+        const int blk = par8 ? CF_BLOCK : CF_BLOCK1;
+        const int grid = grid_for(par8 ? half * 8 : half, blk, n_sm * (par8 ? CF_MINB8 : cf_blocks_per_sm1[nm - 7]));  // at most one resident wave
+        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, blk, cf_smem(nm, par8), a);
         CUDA_TRY(cudaGetLastError());
         st.fr_mul_round += (uint64_t)half * ((nm == 8 ? 20 : 18) + (mk > c ? 1 : 0) + (do_fold ? 4 : 0));
         st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
