@@ -70,39 +70,87 @@ static inline __attribute__((always_inline)) Fr sub(const Fr& x, const Fr& y) {
 static inline Fr neg(const Fr& x) { return sub(zero(), x); }
 static inline Fr dbl(const Fr& x) { return add(x, x); }
 
-// Montgomery product, "no-carry" CIOS (valid because the top limb of q has spare bits: q < 2^254).
+// Montgomery product, "no-carry" CIOS (valid because the top limb of q has spare bits: q < 2^254), written with MULX and
+// two interleaved carry chains (ADCX / ADOX): one row of x*y[i], then one reduction row, four times.  The transcript is a
+// chain of ~2 500 DEPENDENT products per sumcheck round, so what matters here is latency, and gcc's code for the
+// portable form (single ADC chain, spills) is ~1.3x slower.  After every row the running value is < x + q, hence any
+// x < 2q (and any y < 2^256) is a legal input and the unreduced result is < x*y/2^256 + q.
+static const uint64_t ASM_Q[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+static const uint64_t ASM_QINV = 0xc2e1f593efffffffULL;
+
+#define GKR_MAC_ROW0                   \
+    "movq 0(%[y]), %%rdx\n\t"          \
+    "mulx %[x0], %[t0], %[t1]\n\t"     \
+    "mulx %[x1], %%rax, %[t2]\n\t"     \
+    "addq %%rax, %[t1]\n\t"            \
+    "mulx %[x2], %%rax, %[t3]\n\t"     \
+    "adcq %%rax, %[t2]\n\t"            \
+    "mulx %[x3], %%rax, %[A]\n\t"      \
+    "adcq %%rax, %[t3]\n\t"            \
+    "adcq $0, %[A]\n\t"
+#define GKR_MAC_ROW(off)               \
+    "xorl %%eax, %%eax\n\t"            \
+    "movq " #off "(%[y]), %%rdx\n\t"   \
+    "mulx %[x0], %%rax, %[A]\n\t"      \
+    "adox %%rax, %[t0]\n\t"            \
+    "adcx %[A], %[t1]\n\t"             \
+    "mulx %[x1], %%rax, %[A]\n\t"      \
+    "adox %%rax, %[t1]\n\t"            \
+    "adcx %[A], %[t2]\n\t"             \
+    "mulx %[x2], %%rax, %[A]\n\t"      \
+    "adox %%rax, %[t2]\n\t"            \
+    "adcx %[A], %[t3]\n\t"             \
+    "mulx %[x3], %%rax, %[A]\n\t"      \
+    "adox %%rax, %[t3]\n\t"            \
+    "movl $0, %%eax\n\t"               \
+    "adcx %%rax, %[A]\n\t"             \
+    "adox %%rax, %[A]\n\t"
+#define GKR_RED_ROW                    \
+    "movq %[t0], %%rdx\n\t"            \
+    "imulq %[qinv], %%rdx\n\t"         \
+    "xorl %%eax, %%eax\n\t"            \
+    "mulx %[q0], %%rax, %[H]\n\t"      \
+    "adcx %[t0], %%rax\n\t"            \
+    "movq %[H], %[t0]\n\t"             \
+    "adcx %[t1], %[t0]\n\t"            \
+    "mulx %[q1], %%rax, %[t1]\n\t"     \
+    "adox %%rax, %[t0]\n\t"            \
+    "adcx %[t2], %[t1]\n\t"            \
+    "mulx %[q2], %%rax, %[t2]\n\t"     \
+    "adox %%rax, %[t1]\n\t"            \
+    "adcx %[t3], %[t2]\n\t"            \
+    "mulx %[q3], %%rax, %[t3]\n\t"     \
+    "adox %%rax, %[t2]\n\t"            \
+    "movl $0, %%eax\n\t"               \
+    "adcx %%rax, %[t3]\n\t"            \
+    "adox %[A], %[t3]\n\t"
+
+// x*y*2^-256 mod q + {0, q}: in [0, 2q) for x, y < 2q (not canonicalised)
+static inline __attribute__((always_inline)) Fr mul_lazy(const Fr& x, const Fr& y) {
+    uint64_t t0, t1, t2, t3, A, H;
+    asm(GKR_MAC_ROW0 GKR_RED_ROW GKR_MAC_ROW(8) GKR_RED_ROW GKR_MAC_ROW(16) GKR_RED_ROW GKR_MAC_ROW(24) GKR_RED_ROW
+        : [t0] "=&r"(t0), [t1] "=&r"(t1), [t2] "=&r"(t2), [t3] "=&r"(t3), [A] "=&r"(A), [H] "=&r"(H)
+        : [x0] "r"(x.l[0]), [x1] "r"(x.l[1]), [x2] "r"(x.l[2]), [x3] "r"(x.l[3]), [y] "r"(y.l), [q0] "m"(ASM_Q[0]), [q1] "m"(ASM_Q[1]),
+          [q2] "m"(ASM_Q[2]), [q3] "m"(ASM_Q[3]), [qinv] "m"(ASM_QINV), "m"(y)
+        : "rax", "rdx", "cc");
+    return Fr{{t0, t1, t2, t3}};
+}
+#undef GKR_MAC_ROW0
+#undef GKR_MAC_ROW
+#undef GKR_RED_ROW
+// fr.Element.Mul: canonical inputs, canonical output
 static inline __attribute__((always_inline)) Fr mul(const Fr& x, const Fr& y) {
-    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-#define GKR_ROW(yi)                                                \
-    {                                                              \
-        u128 a = (u128)x.l[0] * (yi) + t0;                         \
-        uint64_t lo = (uint64_t)a, A = (uint64_t)(a >> 64);        \
-        uint64_t m = lo * QINV;                                    \
-        u128 c = (u128)m * Q[0] + lo;                              \
-        uint64_t C = (uint64_t)(c >> 64);                          \
-        a = (u128)x.l[1] * (yi) + t1 + A;                          \
-        A = (uint64_t)(a >> 64);                                   \
-        c = (u128)m * Q[1] + (uint64_t)a + C;                      \
-        t0 = (uint64_t)c;                                          \
-        C = (uint64_t)(c >> 64);                                   \
-        a = (u128)x.l[2] * (yi) + t2 + A;                          \
-        A = (uint64_t)(a >> 64);                                   \
-        c = (u128)m * Q[2] + (uint64_t)a + C;                      \
-        t1 = (uint64_t)c;                                          \
-        C = (uint64_t)(c >> 64);                                   \
-        a = (u128)x.l[3] * (yi) + t3 + A;                          \
-        A = (uint64_t)(a >> 64);                                   \
-        c = (u128)m * Q[3] + (uint64_t)a + C;                      \
-        t2 = (uint64_t)c;                                          \
-        C = (uint64_t)(c >> 64);                                   \
-        t3 = C + A;                                                \
-    }
-    GKR_ROW(y.l[0])
-    GKR_ROW(y.l[1])
-    GKR_ROW(y.l[2])
-    GKR_ROW(y.l[3])
-#undef GKR_ROW
-    return reduce_once(t0, t1, t2, t3);
+    const Fr t = mul_lazy(x, y);
+    return reduce_once(t.l[0], t.l[1], t.l[2], t.l[3]);
+}
+// x + y without reduction (caller tracks the bound)
+static inline __attribute__((always_inline)) Fr add_lazy(const Fr& x, const Fr& y) {
+    ull t0, t1, t2, t3;
+    unsigned char c = _addcarry_u64(0, x.l[0], y.l[0], &t0);
+    c = _addcarry_u64(c, x.l[1], y.l[1], &t1);
+    c = _addcarry_u64(c, x.l[2], y.l[2], &t2);
+    (void)_addcarry_u64(c, x.l[3], y.l[3], &t3);
+    return Fr{{t0, t1, t2, t3}};
 }
 static inline __attribute__((always_inline)) Fr sqr(const Fr& x) { return mul(x, x); }
 

@@ -18,15 +18,20 @@ static const Fr ARKS[MIMC_ROUNDS] = {
 
 // hash/mimc.go:31-39 MimcKeyedPermutation.  x^7 is evaluated as x^4 * x^3 with x^3 and x^4 independent
 // (dependency depth 3 instead of the reference's 4-long chain x^2,x^3,x^6,x^7); exact arithmetic, same value.
+// Inside a round the products stay unreduced in [0, 2q): with res < q and key+ark < q,
+//   t = res + (key+ark) < 2q,  t^2 < 1.76q,  t^4 < 1.59q,  t^3 < 1.67q,  t^4*t^3 < 1.50q  (u*v/2^256 + q, q/2^256 = 0.189),
+// so ONE conditional subtraction per round restores res < q; the value mod q is what the reference computes.
 static inline Fr mimc_keyed_permutation(const Fr& x, const Fr& key) {
+    Fr ka[MIMC_ROUNDS];  // key + ark_i: off the multiplication chain
+    for (int i = 0; i < MIMC_ROUNDS; i++) ka[i] = add(key, ARKS[i]);
     Fr res = x;
-    // key + ark_i precomputation would need 91 adds per block; adds are cheap and off the mul chain
     for (int i = 0; i < MIMC_ROUNDS; i++) {
-        Fr t = add(add(res, key), ARKS[i]);
-        Fr t2 = sqr(t);
-        Fr t4 = sqr(t2);
-        Fr t3 = mul(t2, t);
-        res = mul(t4, t3);
+        const Fr t = add_lazy(res, ka[i]);
+        const Fr t2 = mul_lazy(t, t);
+        const Fr t4 = mul_lazy(t2, t2);
+        const Fr t3 = mul_lazy(t2, t);
+        const Fr r = mul_lazy(t4, t3);
+        res = reduce_once(r.l[0], r.l[1], r.l[2], r.l[3]);
     }
     return res;
 }

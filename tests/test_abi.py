@@ -68,6 +68,15 @@ def test_host_transcript_matches_oracle(oracle):
     for n in (0, 1, 3, 9, 91):
         x = oracle.to_mont([int.from_bytes(rng.bytes(40), "little") % oracle.Q for _ in range(n)]).reshape(n, 4)
         assert np.array_equal(gkrb200.common.GetChallenge(x), oracle.mimc_hash(x))
+    # edge residues through the hand-written ADX multiplier and the unreduced in-round products of the host MiMC chain
+    Q = oracle.Q
+    edge = [0, 1, 2, Q - 1, Q - 2, (1 << 256) % Q, Q // 2, Q // 2 + 1, (1 << 253) - 1, Q - (1 << 64), (1 << 64) - 1, (1 << 192)]
+    for rep in range(40):
+        vals = [edge[(rep * 7 + i * 5) % len(edge)] for i in range(1 + rep % 9)]
+        x = oracle.to_mont(vals).reshape(len(vals), 4)
+        assert np.array_equal(gkrb200.common.GetChallenge(x), oracle.mimc_hash(x)), vals
+        raw = np.array([[(v >> (64 * j)) & (2**64 - 1) for j in range(4)] for v in vals], dtype=np.uint64)  # same words read as Montgomery images
+        assert np.array_equal(gkrb200.common.GetChallenge(raw), oracle.mimc_hash(raw)), vals
     assert oracle.from_mont(gkrb200.common.GetChallenge(oracle.to_mont([12])))[0] == \
         1808205620575546259657963589762746470347087906694759866517376279978241663265  # hash/hash_test.go:21-27
     for n in range(1, 13):
