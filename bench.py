@@ -138,11 +138,13 @@ NCU_TRAFFIC = {22: 272.7e6}
 NCU_TRAFFIC_NOTE = "ncu capture of the round-0 launch of one layer (2^21 pairs: 268.4 MB algorithmic); `achieved` averages all 1564 launches of a proof"
 
 
-def workload_config(args, world, P=1):
+def workload_config(args, world, P=1, replicas=False):
     return {
         "workload": "full MiMC GKR proof (Circuit.Assign + gkr.Prove, 94 layers, transcript bit-exact) of a 2^%d-hash batch over BN254 Fr" % args.bn,
-        "bn": args.bn, "hashes_per_step": 1 << args.bn, "proof_elements": 1006 * args.bn + 183,
-        "parallelism": "single GPU, %d proofs in flight" % P if world == 1 else "batch sharded on low address bits over %d GPUs, NCCL all-gather of the round polynomials, %d proofs in flight" % (world, P),
+        "bn": args.bn, "hashes_per_step": (1 << args.bn) * (world if replicas else 1), "proof_elements": 1006 * args.bn + 183,
+        "parallelism": "single GPU, %d proofs in flight" % P if world == 1 else (
+            "replicas: each of the %d GPUs proves its own 2^%d batches, no exchange, %d proofs in flight per GPU" % (world, args.bn, P) if replicas else
+            "batch sharded on low address bits over %d GPUs, NCCL all-gather of the round polynomials, %d proofs in flight" % (world, P)),
         "l2": "inputs larger than L2: 93 layer tables of %d MiB each per proof" % ((32 << args.bn) >> 20),
         "seeds": [args.seed, args.seed + 1, args.seed + 2],
     }
@@ -159,7 +161,10 @@ def main():
     ap.add_argument("--cpu-bn", type=int, default=18, help="batch of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0x6B6B72)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=0, help="proofs in flight per GPU (0 = auto: 2 on one GPU, 1 when sharded)")
+    ap.add_argument("--inflight", type=int, default=0, help="proofs in flight per GPU (0 = auto: up to 3, bounded by host cores per rank)")
+    ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
+                    help="N > 1 GPUs: 'sharded' = every 2^bn batch is split over all N GPUs (one proof, round sums exchanged; the north-star "
+                         "configuration, strong scaling); 'replicas' = every GPU proves its own 2^bn batches (no exchange, weak scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -208,13 +213,17 @@ def main():
     n, bn = 1 << args.bn, args.bn
     # P proofs in flight: each has its own context (arena + stream) and its own host thread, so the serial host
     # transcript of one proof (MiMC challenges, ~130 ms per 2^22 proof) overlaps the device rounds of another.
-    P = args.inflight if args.inflight > 0 else (3 if world == 1 else 2)
+    replicas = world > 1 and args.mode == "replicas"
+    sharded = world > 1 and not replicas
+    cores = os.cpu_count() or 1
+    # every pipeline keeps one host thread busy (transcript or spinning on the result slot): stay within the cores a rank can have
+    P = args.inflight if args.inflight > 0 else max(1, min(3, cores // world))
     main_stream = torch.cuda.Stream()
     streams = [torch.cuda.Stream() for _ in range(P)]  # the library launches on these; events are recorded on main_stream after joining them
     torch.cuda.set_stream(main_stream)
     ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream) for st_ in streams]
     ctx = ctxs[0]
-    if world > 1:
+    if sharded:
         for c in ctxs:  # one communicator per pipeline, created in the same order on every rank
             uid = [gkrb200.Context.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
@@ -342,11 +351,12 @@ def main():
 
     if rank == 0:
         ms_step = ms_total / args.steps
+        n_step = n * (world if replicas else 1)  # hashes proven per step over all ranks
         line = {
-            "metric": METRIC, "value": n / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr, Montgomery)",
-            "data": "synthetic", "config": workload_config(args, world, P), "clocks": clocks,
-            "e2e": {"value": n / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "metric": METRIC, "value": n_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr, Montgomery)",
+            "data": "synthetic", "config": workload_config(args, world, P, replicas), "clocks": clocks,
+            "e2e": {"value": n_step / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roofline, "roofline_int": roofline_int, "kernels_profile_step": kernels,

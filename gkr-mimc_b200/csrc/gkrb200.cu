@@ -168,6 +168,7 @@ struct gkrb200_ctx {
     bool force_generic = false;  // test hook: run cipher layers through the generic evaluate-at-9-points kernel
     int exchange_and_fetch(int nacc, H::Fr* out);
     int exchange_and_fetch_wide(int nm, int wl, H::Fr* out);
+    int mle_eval(const FrRaw* table, int bn_total, const H::Fr* point, bool use_shards, H::Fr* out);
     int fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX_FWD]);
     int tail_len = TAIL_MAX_FWD;     // option: residual length (entries over all ranks) handed to the host
     int sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn_total, const H::Fr* q, const H::Fr* trusted_claim, const H::Fr& ark, bool use_shards,
@@ -1032,6 +1033,214 @@ extern "C" int gkrb200_gkr_prove_mimc(gkrb200_ctx* c, const uint64_t* qprime, in
     if (cur != gkrb200_proof_vec_len(bn)) return fail(GKRB200_ERR_STATE, "internal: proof vector length %zu != %zu", cur, gkrb200_proof_vec_len(bn));
     if (flags & GKRB200_PROOF_REGULAR)
         for (size_t i = 0; i < cur; i++) out[i] = H::from_mont(out[i]);
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ hint I/O
+extern "C" int gkrb200_convert(gkrb200_ctx* c, const uint64_t* in, size_t n, uint64_t* out, int to_mont) {
+    if (!c || (n && (!in || !out))) return fail(GKRB200_ERR_ARG, "null argument");
+    if (n == 0) return 0;
+    CUDA_TRY(cudaSetDevice(c->device));
+    FrRaw* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, n * sizeof(FrRaw)));
+    int rc = c->upload(d, in, n);
+    if (!rc) {
+        LAUNCH(c, KC_STAGING, gkr::k_convert, grid_for(n, 256, c->n_sm * 8), 256, 0, d, d, n, to_mont ? 1 : 0);
+        cudaError_t e = cudaMemcpyAsync(out, d, n * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(GKRB200_ERR_CUDA, "convert: %s", cudaGetErrorString(e));
+        c->st.d2h_bytes += n * sizeof(FrRaw);
+    }
+    cudaFree(d);
+    return rc;
+}
+
+extern "C" int gkrb200_mimc_assign_ex(gkrb200_ctx* c, const uint64_t* key, const uint64_t* msg, size_t n, uint64_t* out, uint32_t flags) {
+    int bn;
+    TRY(check_n(c, n, &bn));
+    if (!key || !msg) return fail(GKRB200_ERR_ARG, "null input table");
+    if (flags & ~(GKRB200_IO_INPUT_REGULAR | GKRB200_IO_OUTPUT_REGULAR | GKRB200_IO_OUTPUT_HASH)) return fail(GKRB200_ERR_ARG, "unknown flags 0x%x", flags);
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->sharded = c->world > 1 && bn > c->log_world;
+    c->bn = bn;
+    if (!c->sharded) {
+        c->n_local = n;
+        TRY(c->upload(c->slot(0), key, n));
+        TRY(c->upload(c->slot(1), msg, n));
+    } else {
+        c->n_local = n / (size_t)c->world;
+        FrRaw* tmp_key = c->eq;
+        FrRaw* tmp_msg = c->scratch[0];
+        TRY(c->upload(tmp_key, key, n));
+        TRY(c->upload(tmp_msg, msg, n));
+        const int grid = grid_for(c->n_local, 256, c->n_sm * 8);
+        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_key, c->slot(0), c->n_local, c->world, c->rank);
+        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_msg, c->slot(1), c->n_local, c->world, c->rank);
+    }
+    if (flags & GKRB200_IO_INPUT_REGULAR) {  // SetBigInt of every input on the device (prover/gadget/hints.go:202-205)
+        const int grid = grid_for(c->n_local, 256, c->n_sm * 8);
+        LAUNCH(c, KC_STAGING, gkr::k_convert, grid, 256, 0, c->slot(0), c->slot(0), c->n_local, 1);
+        LAUNCH(c, KC_STAGING, gkr::k_convert, grid, 256, 0, c->slot(1), c->slot(1), c->n_local, 1);
+    }
+    TRY(assign_common(c, c->n_local));
+    if (out) {
+        const FrRaw* src = c->slot(93);
+        if (flags & (GKRB200_IO_OUTPUT_REGULAR | GKRB200_IO_OUTPUT_HASH)) {
+            LAUNCH(c, KC_STAGING, gkr::k_hash_out, grid_for(c->n_local, 256, c->n_sm * 8), 256, 0, c->slot(93), c->slot(0), c->slot(1), c->eq, c->n_local,
+                   (flags & GKRB200_IO_OUTPUT_HASH) ? 1 : 0, (flags & GKRB200_IO_OUTPUT_REGULAR) ? 1 : 0);
+            src = c->eq;
+        }
+        CUDA_TRY(cudaMemcpyAsync(out, src, c->n_local * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
+        c->st.d2h_bytes += c->n_local * sizeof(FrRaw);
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ MultiLin.Evaluate on the device
+// poly/multilin.go:59-66: fold a copy of the table with point[0], point[1], ... (MSB first).  The first fold is out of place
+// (the table is never modified), the rest in place in a scratch table; the last <= 32 entries are finished on the host.
+int gkrb200_ctx::mle_eval(const FrRaw* table, int bn, const H::Fr* point, bool use_shards, H::Fr* out) {
+    const int W = use_shards ? world : 1, LW = use_shards ? log_world : 0;
+    const int bnl = bn - LW;
+    int tail_bits = 0;
+    while (((size_t)2 << tail_bits) * (size_t)W <= (size_t)TAIL_MAX && tail_bits < bnl) tail_bits++;
+    const int kdev = bnl - tail_bits;  // folds on the device; the last of them is done by fetch_residual
+    const FrRaw* cur = table;
+    FrRaw* dst = scratch[0];
+    size_t len = (size_t)1 << bnl;
+    for (int k = 0; k + 1 < kdev; k++) {
+        gkr::FoldArgs f{};
+        f.n_tables = 1;
+        f.src[0] = cur;
+        f.dst[0] = dst;
+        f.half = len / 2;
+        memcpy(&f.r, &point[k], 32);
+        LAUNCH(this, KC_FOLD, gkr::k_fold, grid_for(f.half, 256, n_sm * 8), 256, 0, f);
+        cur = dst;
+        len /= 2;
+    }
+    CUDA_TRY(cudaGetLastError());
+    H::Fr tabs[1][TAIL_MAX];
+    const FrRaw* curp[1] = {cur};
+    TRY(fetch_residual(curp, 1, (size_t)1 << tail_bits, kdev > 0, kdev > 0 ? point[kdev - 1] : H::zero(), W, tabs));
+    size_t rl = ((size_t)1 << tail_bits) * (size_t)W;
+    for (int k = kdev; k < bn; k++) {
+        host_fold(tabs[0], rl, point[k]);
+        rl /= 2;
+    }
+    *out = tabs[0][0];
+    return 0;
+}
+
+extern "C" int gkrb200_assign_layer_evaluate(gkrb200_ctx* c, int layer, const uint64_t* point, int bn, uint64_t* out) {
+    if (!c || !out || layer < 0 || layer >= N_LAYERS || (bn > 0 && !point)) return fail(GKRB200_ERR_ARG, "bad argument");
+    if (c->bn < 0) return fail(GKRB200_ERR_STATE, "no assignment in this context");
+    if (bn != c->bn) return fail(GKRB200_ERR_ARG, "the assignment has 2^%d entries, the point has %d coordinates", c->bn, bn);
+    CUDA_TRY(cudaSetDevice(c->device));
+    H::Fr r;
+    TRY(c->mle_eval(c->slot(layer), bn, (const H::Fr*)point, c->sharded, &r));
+    memcpy(out, &r, 32);
+    return 0;
+}
+
+extern "C" int gkrb200_mle_evaluate(gkrb200_ctx* c, const uint64_t* table, size_t n, const uint64_t* point, uint64_t* out) {
+    int bn;
+    TRY(check_n(c, n, &bn));
+    if (!table || !out || (bn > 0 && !point)) return fail(GKRB200_ERR_ARG, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    FrRaw* d = c->eq;  // cap entries: the table is staged in the eq slot, folded into scratch[0]
+    TRY(c->upload(d, table, n));
+    H::Fr r;
+    TRY(c->mle_eval(d, bn, (const H::Fr*)point, false, &r));
+    memcpy(out, &r, 32);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ gkr.Verify (gkr/verifier.go:15-132)
+// sumcheck.Verify (sumcheck/verifier.go:28-65): returns false (with a message) when a round check fails
+static bool sumcheck_verify(const H::Fr* claims, size_t n_claims, const H::Fr* proof, int bn, int nco, H::Fr* challenges, H::Fr* final_claim,
+                            H::Fr* recomb, char* why, size_t why_len) {
+    // recombineMultiClaims (:58-65): always hashes the claims (the len < 1 guard of the reference cannot trigger)
+    *recomb = H::mimc_hash(claims, n_claims);
+    H::Fr expected = H::eval_univariate(claims, n_claims, *recomb);
+    const H::Fr zero = H::zero(), one = H::one();
+    for (int i = 0; i < bn; i++) {
+        const H::Fr* p = proof + (size_t)i * nco;
+        const H::Fr actual = H::add(H::eval_univariate(p, nco, zero), H::eval_univariate(p, nco, one));
+        if (!H::eq(expected, actual)) {
+            snprintf(why, why_len, "at round %d verifier eval at 0 + 1 differs from the expected value", i);
+            return false;
+        }
+        challenges[i] = H::mimc_hash(p, nco);
+        expected = H::eval_univariate(p, nco, challenges[i]);
+    }
+    *final_claim = expected;
+    return true;
+}
+
+extern "C" int gkrb200_gkr_verify_mimc(gkrb200_ctx* c, const uint64_t* proof_vec, int bn, const uint64_t* qprime, uint32_t flags) {
+    if (!c || !proof_vec || (bn > 0 && !qprime)) return fail(GKRB200_ERR_ARG, "null argument");
+    if (c->bn < 0) return fail(GKRB200_ERR_STATE, "gkr_verify_mimc needs the assignment (inputs and outputs) in the context");
+    if (bn != c->bn) return fail(GKRB200_ERR_ARG, "inconsistent sizes : bn is %d but the assignment has 2^%d entries", bn, c->bn);
+    CUDA_TRY(cudaSetDevice(c->device));
+    const size_t ubn = (size_t)bn, total = gkrb200_proof_vec_len(bn);
+    std::vector<H::Fr> vec(total);
+    memcpy(vec.data(), proof_vec, total * 32);
+    if (flags & GKRB200_PROOF_REGULAR)
+        for (auto& v : vec) v = H::to_mont(v);
+    // slice the flat vector (prover/gadget/hints.go:275-317 GkrProofFromVec order)
+    const H::Fr *sc[N_LAYERS], *cl[N_LAYERS], *qp[N_LAYERS];
+    size_t cur = 0;
+    for (int l = 0; l < N_LAYERS; l++) { sc[l] = vec.data() + cur; cur += ubn * (size_t)n_coeffs(l); }
+    for (int l = 0; l < N_LAYERS; l++) { cl[l] = vec.data() + cur; cur += (size_t)n_out(l); }
+    for (int l = 0; l < N_LAYERS; l++) { qp[l] = vec.data() + cur; cur += (size_t)(l == N_LAYERS - 1 ? 1 : n_out(l)) * ubn; }
+    // gkr/verifier.go:25: the initial qPrime must be the one in the proof
+    if (bn && memcmp(qprime, qp[N_LAYERS - 1], ubn * 32) != 0) return fail(GKRB200_ERR_VERIFY, "initial qPrime does not match with the proof");
+    // :36 the initial claim is the output MLE at qPrime (the prover does not send it)
+    H::Fr out_claim;
+    TRY(c->mle_eval(c->slot(N_LAYERS - 1), bn, (const H::Fr*)qprime, c->sharded, &out_claim));
+    std::vector<H::Fr> challenges(ubn + 1), tmp(MAX_CLAIMS);
+    char why[160];
+    for (int layer = N_LAYERS - 1; layer >= 0; layer--) {
+        int in[2];
+        const int k = layer_in(layer, in);
+        if (k == 0) break;  // :40-44
+        const bool top = layer == N_LAYERS - 1;
+        const size_t n_cl = top ? 1 : (size_t)n_out(layer), n_q = top ? 1 : (size_t)n_out(layer);
+        const H::Fr* claims = top ? &out_claim : cl[layer];
+        H::Fr final_claim, recomb;
+        if (!sumcheck_verify(claims, n_cl, sc[layer], bn, n_coeffs(layer), challenges.data(), &final_claim, &recomb, why, sizeof why))
+            return fail(GKRB200_ERR_VERIFY, "error at sumcheck layer %d : %s", layer, why);
+        // testSumcheck (:61-117)
+        H::Fr sub[2];
+        for (int i = 0; i < k; i++) {
+            const int at = pos_in_out(in[i], layer);
+            if (bn && memcmp(qp[in[i]] + (size_t)at * ubn, challenges.data(), ubn * 32) != 0)
+                return fail(GKRB200_ERR_VERIFY, "mismatch for qPrimes between sumcheck and proof at layer %d", layer);
+            sub[i] = cl[in[i]][at];
+        }
+        H::Fr expected;
+        if (layer == 2) {
+            expected = sub[0];  // IdentityGate.Eval (circuit/gates/copy.go:20-22)
+        } else {            // CipherGate.Eval (circuit/gates/cipher.go:45-55)
+            const H::Fr t = H::add(H::add(sub[0], sub[1]), H::ARKS[layer - 3]);
+            const H::Fr t2 = H::sqr(t);
+            expected = H::mul(H::sqr(H::mul(t2, t)), t);
+        }
+        for (size_t i = 0; i < n_q; i++) tmp[i] = H::eval_eq(qp[layer] + i * ubn, challenges.data(), ubn);
+        const H::Fr eq_eval = H::eval_univariate(tmp.data(), n_q, recomb);
+        expected = H::mul(expected, eq_eval);
+        if (!H::eq(expected, final_claim))
+            return fail(GKRB200_ERR_VERIFY, "the expected claim and the final claim of the sumcheck do not match for layer %d", layer);
+    }
+    // testInitialRound (:120-132) for the two input layers
+    for (int layer = 0; layer < 2; layer++) {
+        H::Fr actual;
+        TRY(c->mle_eval(c->slot(layer), bn, qp[layer], c->sharded, &actual));
+        if (!H::eq(actual, cl[layer][0])) return fail(GKRB200_ERR_VERIFY, "input layer check failed (layer %d)", layer);
+    }
     return 0;
 }
 

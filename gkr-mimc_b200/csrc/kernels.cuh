@@ -797,6 +797,38 @@ __global__ void k_sum_ranks(const FrRaw* __restrict__ all, int G, int nacc, FrRa
 }
 
 // ------------------------------------------------------------------------------------------------
+// Hint I/O (prover/gadget/hints.go:197-233): batched Montgomery <-> regular conversion and the user-visible hash
+// ------------------------------------------------------------------------------------------------
+// out[i] = to_mont ? in[i]*2^256 mod q (fr.Element.SetBigInt of a reduced value) : in[i]*2^-256 mod q (ToBigIntRegular)
+__global__ void __launch_bounds__(256) k_convert(const FrRaw* __restrict__ in, FrRaw* __restrict__ out, size_t n, int to_mont) {
+    Fr f = fr_zero();
+    if (to_mont) {  // R^2 mod q
+        f.v[0] = 0xae216da7u; f.v[1] = 0x1bb8e645u; f.v[2] = 0xe35c59e3u; f.v[3] = 0x53fe3ab1u;
+        f.v[4] = 0x53bb8085u; f.v[5] = 0x8c49833du; f.v[6] = 0x7f4e44a5u; f.v[7] = 0x0216d0b1u;
+    } else {
+        f.v[0] = 1;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        fr_store(out + i, fr_mulc(fr_load_stream(in + i), f));
+}
+// out[x] = a93[x] (+ 2*key[x] + msg[x] when hash != 0: hash.MimcUpdateInplace, hash/mimc.go:24-28 / gadget_api.go:28), optionally
+// in regular form
+__global__ void __launch_bounds__(256) k_hash_out(const FrRaw* __restrict__ a93, const FrRaw* __restrict__ key, const FrRaw* __restrict__ msg,
+                                                   FrRaw* __restrict__ out, size_t n, int hash, int regular) {
+    Fr one_raw = fr_zero();
+    one_raw.v[0] = 1;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        Fr v = fr_load_stream(a93 + x);
+        if (hash) {
+            const Fr k = fr_load_stream(key + x);
+            v = fr_add(fr_add(v, fr_dbl(k)), fr_load_stream(msg + x));
+        }
+        if (regular) v = fr_mulc(v, one_raw);
+        fr_store(out + x, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // element-wise ops for arithmetic parity tests
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fr_batch(int op, const FrRaw* __restrict__ a, const FrRaw* __restrict__ b, FrRaw* __restrict__ out, size_t n) {

@@ -70,6 +70,11 @@ def lib():
     L.gkrb200_stats_reset.argtypes = [vp]
     L.gkrb200_stats_get.argtypes = [vp, ctypes.POINTER(Stats)]
     L.gkrb200_set_profiling.argtypes = [vp, i32]
+    L.gkrb200_mimc_assign_ex.argtypes = [vp, vp, vp, sz, vp, u32]
+    L.gkrb200_convert.argtypes = [vp, vp, sz, vp, i32]
+    L.gkrb200_mle_evaluate.argtypes = [vp, vp, sz, vp, vp]
+    L.gkrb200_assign_layer_evaluate.argtypes = [vp, i32, vp, i32, vp]
+    L.gkrb200_gkr_verify_mimc.argtypes = [vp, vp, i32, vp, u32]
     L.gkrb200_set_option.argtypes = [vp, i32, ctypes.c_long]
     L.gkrb200_microbench.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = L

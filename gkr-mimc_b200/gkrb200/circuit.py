@@ -28,6 +28,13 @@ class Assignment:
         check(lib().gkrb200_assign_layer_to_host(self.ctx.handle, layer, _p(out), self.n_local))
         return out
 
+    def Evaluate(self, layer, coords):
+        """a[layer].Evaluate(coords) (poly/multilin.go:59-66) without moving the layer off the device"""
+        q = fr_array(coords).reshape(-1, 4) if self.bn else None
+        out = fr_empty(1)
+        check(lib().gkrb200_assign_layer_evaluate(self.ctx.handle, layer, _p(q), self.bn, _p(out)))
+        return out[0]
+
 
 class MimcCircuit:
     """examples.MimcCircuit() (examples/mimc.go:10-37) bound to a device context."""
@@ -72,6 +79,23 @@ class MimcCircuit:
         a = Assignment(self.ctx, n_local, bn)
         if want_outputs:
             a.outputs = out93
+        return a
+
+    IO_INPUT_REGULAR, IO_OUTPUT_REGULAR, IO_OUTPUT_HASH = 1, 2, 4
+
+    def AssignEx(self, key, msg, flags):
+        """The hint's view of Assign (prover/gadget/hints.go:135-145,197-233): inputs optionally in regular form (SetBigInt on the
+        device), and `outputs` = layer 93 or the gadget's hash a[93] + 2*key + msg, optionally in regular form."""
+        k = fr_array(key).reshape(-1, 4)
+        m = fr_array(msg).reshape(-1, 4)
+        if k.shape != m.shape:
+            raise ValueError("inputs must have the same length")
+        n = k.shape[0]
+        bn, n_local = self._shape(n)
+        out = fr_empty(n_local)
+        check(lib().gkrb200_mimc_assign_ex(self.ctx.handle, _p(k), _p(m), n, _p(out), flags))
+        a = Assignment(self.ctx, n_local, bn)
+        a.outputs = out
         return a
 
     def AssignDevice(self, d_key_ptr, d_msg_ptr, n):

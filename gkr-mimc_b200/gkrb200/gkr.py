@@ -39,3 +39,13 @@ def Prove(c, a, qPrime, regular=False):
     vec = fr_empty(int(lib().gkrb200_proof_vec_len(bn)))
     check(lib().gkrb200_gkr_prove_mimc(c.ctx.handle, _p(q), bn, _p(vec), PROOF_REGULAR if regular else PROOF_MONTGOMERY))
     return Proof(c, bn, vec)
+
+
+def Verify(c, a, proof, qPrime, regular=False):
+    """gkr.Verify(c, proof, inputs, outputs, qPrime) (gkr/verifier.go:15-59) against the assignment held by c.ctx (inputs = layers
+    0 and 1, outputs = layer 93, evaluated on the device).  Returns None when the proof is accepted, raises GkrB200Error otherwise
+    (the reference returns an error value)."""
+    bn = a.bn
+    q = fr_array(qPrime).reshape(-1, 4) if bn else None
+    vec = fr_array(proof.to_vec() if isinstance(proof, Proof) else proof)
+    check(lib().gkrb200_gkr_verify_mimc(c.ctx.handle, _p(vec), bn, _p(q), PROOF_REGULAR if regular else PROOF_MONTGOMERY))

@@ -37,3 +37,20 @@ def InterpolateOnRange(values):
     out = fr_empty(v.shape[0])
     check(lib().gkrb200_interpolate(_p(v), v.shape[0], _p(out)))
     return out
+
+
+def Evaluate(ctx, table, coords):
+    """MultiLin.Evaluate (poly/multilin.go:59-66) on the device"""
+    t = fr_array(table).reshape(-1, 4)
+    q = fr_array(coords).reshape(-1, 4) if t.shape[0] > 1 else None
+    out = fr_empty(1)
+    check(lib().gkrb200_mle_evaluate(ctx.handle, _p(t), t.shape[0], _p(q), _p(out)))
+    return out[0]
+
+
+def Convert(ctx, values, to_montgomery):
+    """batched fr.Element.SetBigInt / ToBigIntRegular on the device"""
+    v = fr_array(values).reshape(-1, 4)
+    out = fr_empty(v.shape[0])
+    check(lib().gkrb200_convert(ctx.handle, _p(v), v.shape[0], _p(out), 1 if to_montgomery else 0))
+    return out

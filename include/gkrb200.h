@@ -30,7 +30,8 @@ typedef enum {
     GKRB200_ERR_CUDA = -2,   /* CUDA runtime error or no device */
     GKRB200_ERR_OOM = -3,    /* batch larger than the context was sized for (poly/pool.go:70-72 analogue) */
     GKRB200_ERR_COMM = -4,   /* NCCL / multi-GPU error */
-    GKRB200_ERR_STATE = -5   /* call order (e.g. prove before assign) */
+    GKRB200_ERR_STATE = -5,  /* call order (e.g. prove before assign) */
+    GKRB200_ERR_VERIFY = -6  /* gkrb200_gkr_verify_mimc: the proof was rejected (message says where) */
 } gkrb200_status;
 
 /* circuit.Gate implementations that can cross the ABI (circuit/gates.go:9-21):
@@ -74,6 +75,30 @@ int gkrb200_mimc_assign_device(gkrb200_ctx *ctx, const void *d_key, const void *
 
 /* Assignment[layer] -> host (what Go code reads as a[layer]); local shard when multi-GPU.              */
 int gkrb200_assign_layer_to_host(gkrb200_ctx *ctx, int layer, uint64_t *dst, size_t n);
+
+/* ---- the production caller's view: GkrProverHint.Call / HashHint.Call
+ *      (prover/gadget/hints.go:135-145,197-233) hand over big.Int values in REGULAR form and want regular words back.
+ * flags: GKRB200_IO_INPUT_REGULAR  key/msg are regular-form words (reduced mod q): SetBigInt on the device (hints.go:202-205)
+ *        GKRB200_IO_OUTPUT_REGULAR out is written in regular form (ToBigIntRegular)
+ *        GKRB200_IO_OUTPUT_HASH    out[x] = a[93][x] + 2*key[x] + msg[x], the hash the gadget exposes
+ *                                  (hash.MimcUpdateInplace hash/mimc.go:24-28, prover/gadget/gadget_api.go:28): one batched
+ *                                  call replaces N sequential HashHint.Call's and feeds the same assignment to the prover. */
+#define GKRB200_IO_INPUT_REGULAR 1u
+#define GKRB200_IO_OUTPUT_REGULAR 2u
+#define GKRB200_IO_OUTPUT_HASH 4u
+int gkrb200_mimc_assign_ex(gkrb200_ctx *ctx, const uint64_t *key, const uint64_t *msg, size_t n, uint64_t *out, uint32_t flags);
+/* batched fr.Element.SetBigInt (to_montgomery != 0) / ToBigIntRegular on the device; in == out allowed */
+int gkrb200_convert(gkrb200_ctx *ctx, const uint64_t *in, size_t n, uint64_t *out, int to_montgomery);
+
+/* ---- verifier side helpers (gkr/verifier.go:15-132), for the hint's self-check (hints.go:225-229) and for tests ----
+ * MultiLin.Evaluate (poly/multilin.go:59-66) of a host table / of a layer of the assignment held by ctx (no copy);
+ * multi-GPU: collective, the point is over all bn variables.                                                      */
+int gkrb200_mle_evaluate(gkrb200_ctx *ctx, const uint64_t *table, size_t n, const uint64_t *point, uint64_t *out);
+int gkrb200_assign_layer_evaluate(gkrb200_ctx *ctx, int layer, const uint64_t *point, int bn, uint64_t *out);
+/* gkr.Verify(c, proof, inputs, outputs, qPrime) for the MiMC circuit against the assignment held by ctx (inputs =
+ * layers 0 and 1, outputs = layer 93, evaluated on the device).  proof_vec as produced by gkrb200_gkr_prove_mimc with the
+ * same flags.  Returns 0 when the proof is accepted, GKRB200_ERR_VERIFY otherwise.                               */
+int gkrb200_gkr_verify_mimc(gkrb200_ctx *ctx, const uint64_t *proof_vec, int bn, const uint64_t *qprime, uint32_t flags);
 
 /* ---- gkr.Prove(c, a, qPrime)  (gkr/prover.go:21-91) for the MiMC circuit --------------------------------
  * Uses the assignment held by ctx.  proof_vec_out receives 1006*bn+183 elements in the order of

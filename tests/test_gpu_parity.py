@@ -381,3 +381,84 @@ def test_host_tail_length_does_not_change_the_proof(ctx, oracle, tail_len):
             assert all(np.array_equal(g, e) for g, e in zip(got, exp)), bn
     finally:
         ctx.set_option(ctx.OPT_HOST_TAIL_LEN, 32)
+
+
+# ----------------------------------------------------------------------------- the hint's view and the verifier
+@pytest.mark.parametrize("bn", [0, 1, 4, 6, 11, 16])
+def test_mle_evaluate_matches_oracle(ctx, oracle, bn):
+    """MultiLin.Evaluate (poly/multilin.go:59-66) on the device: host table and a layer of the resident assignment"""
+    import gkrb200
+    rng = np.random.default_rng(5000 + bn)
+    n = 1 << bn
+    t, pt = rand_fr(rng, n), rand_fr(rng, bn)
+    assert np.array_equal(gkrb200.poly.Evaluate(ctx, t, pt), oracle.evaluate(t, pt))
+    if bn <= 11:
+        c = gkrb200.MimcCircuit(ctx)
+        key, msg = rand_fr(rng, n), rand_fr(rng, n)
+        a = c.Assign(key, msg)
+        exp = oracle.mimc_assign(key, msg)
+        for layer in (0, 1, 2, 17, 93):
+            assert np.array_equal(a.Evaluate(layer, pt), oracle.evaluate(exp[layer], pt)), layer
+
+
+@pytest.mark.parametrize("bn", [0, 3, 10])
+def test_hint_io_regular_form_and_batched_hash(ctx, oracle, bn):
+    """GkrProverHint.Call / HashHint.Call (prover/gadget/hints.go:135-145,197-233): regular-form inputs converted on the device,
+    regular-form outputs, and the gadget's hash a[93] + 2*key + msg == MimcUpdateInplace(state=key, block=msg) (hash/mimc.go:24-28)"""
+    import gkrb200
+    rng = np.random.default_rng(6000 + bn)
+    n = 1 << bn
+    key_m, msg_m = rand_fr(rng, n), rand_fr(rng, n)
+    key_r, msg_r = gkrb200.common.FromMontgomery(key_m), gkrb200.common.FromMontgomery(msg_m)
+    assert np.array_equal(gkrb200.poly.Convert(ctx, key_m, False), key_r)
+    assert np.array_equal(gkrb200.poly.Convert(ctx, key_r, True), key_m)
+    c = gkrb200.MimcCircuit(ctx)
+    exp93 = oracle.mimc_assign(key_m, msg_m)[93]
+    a = c.AssignEx(key_r, msg_r, c.IO_INPUT_REGULAR)
+    assert np.array_equal(a.outputs, exp93) and np.array_equal(a[0], key_m) and np.array_equal(a[1], msg_m)
+    a = c.AssignEx(key_m, msg_m, c.IO_OUTPUT_REGULAR)
+    assert np.array_equal(a.outputs, gkrb200.common.FromMontgomery(exp93))
+    a = c.AssignEx(key_r, msg_r, c.IO_INPUT_REGULAR | c.IO_OUTPUT_HASH)
+    for x in range(0, n, max(1, n // 7)):
+        # MimcHash([msg]) from state key: s + (Perm_s(b) + s) + b
+        h = oracle.fr_add(oracle.fr_add(oracle.fr_add(exp93[x], key_m[x]), key_m[x]), msg_m[x])
+        assert np.array_equal(a.outputs[x], h)
+    if n == 1:  # state 0: the plain MimcHash of one block (common/challenge.go:10)
+        z = np.zeros((1, 4), dtype=np.uint64)
+        a = c.AssignEx(z, msg_m, c.IO_OUTPUT_HASH)
+        assert np.array_equal(a.outputs[0], oracle.mimc_hash(msg_m))
+    # the proof of an assignment built from regular inputs is the same proof
+    qprime = rand_fr(rng, bn)
+    a = c.AssignEx(key_r, msg_r, c.IO_INPUT_REGULAR)
+    assert np.array_equal(gkrb200.gkr.Prove(c, a, qprime).to_vec(), oracle.assign_and_prove_mimc(key_m, msg_m, qprime)[1])
+
+
+@pytest.mark.parametrize("bn", [0, 1, 5, 9])
+def test_device_backed_verifier_accepts_and_rejects(ctx, oracle, bn):
+    """gkr.Verify (gkr/verifier.go:15-132) with the input/output MLE evaluations on the device: accepts the prover's proof
+    (Montgomery and regular words), agrees with the oracle's verifier on tampered proofs"""
+    import gkrb200
+    rng = np.random.default_rng(7000 + bn)
+    n = 1 << bn
+    key, msg, qprime = rand_fr(rng, n), rand_fr(rng, n), rand_fr(rng, bn)
+    c = gkrb200.MimcCircuit(ctx)
+    a = c.Assign(key, msg, want_outputs=True)
+    proof = gkrb200.gkr.Prove(c, a, qprime)
+    gkrb200.gkr.Verify(c, a, proof, qprime)
+    gkrb200.gkr.Verify(c, a, gkrb200.gkr.Prove(c, a, qprime, regular=True), qprime, regular=True)
+    vec = proof.to_vec()
+    L = vec.shape[0]
+    for pos in sorted({0, 5, L // 3, L - 200 if L > 200 else 1, L - 1} if bn else {0, 90, L - 1}):
+        bad = vec.copy()
+        bad[pos % L, 1] ^= np.uint64(4)
+        oracle_rejects = oracle.gkr_verify_mimc(bad, key, msg, a.outputs, qprime) != 0
+        try:
+            gkrb200.gkr.Verify(c, a, bad, qprime)
+            ours_rejects = False
+        except gkrb200.GkrB200Error as e:
+            ours_rejects = True
+            assert e.code == -6
+        assert ours_rejects == oracle_rejects, pos
+    if bn:
+        with pytest.raises(gkrb200.GkrB200Error):
+            gkrb200.gkr.Verify(c, a, proof, rand_fr(rng, bn))  # another qPrime

@@ -30,6 +30,20 @@ for bn in list(range(0, 9)) + [max_bn]:
     good = np.array_equal(vec, evec) and np.array_equal(a.outputs, exp_out)
     if good and rank == 0:
         good = coracle.gkr_verify_mimc(vec, key, msg, out93, q) == 0
+    if good:  # device-backed verifier and MLE evaluation of sharded layers (collective calls)
+        try:
+            gkrb200.gkr.Verify(c, a, vec, q)
+            bad = vec.copy(); bad[3, 0] ^= np.uint64(1)
+            try:
+                gkrb200.gkr.Verify(c, a, bad, q); good = False
+            except gkrb200.GkrB200Error:
+                pass
+            pt = gkrb200.common.RandomFrArray(bn + 3)[3:]
+            full = coracle.mimc_assign(key, msg)
+            for layer in (0, 50, 93):
+                good = good and np.array_equal(a.Evaluate(layer, pt), coracle.evaluate(full[layer], pt))
+        except gkrb200.GkrB200Error as e:
+            print("rank %d: verifier rejected: %s" % (rank, e), flush=True); good = False
     t = torch.tensor([1 if good else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
