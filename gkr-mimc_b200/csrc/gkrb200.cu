@@ -117,7 +117,7 @@ struct gkrb200_ctx {
     FrRaw* d_all = nullptr;      // [8*64]
     FrRaw* d_resid = nullptr;    // [3][TAIL_MAX] residual tables after the last device fold
     int cf_blocks_per_sm1[2] = {CF_MINB1_FWD, CF_MINB1_FWD};
-    uint32_t* partials_w = nullptr;  // [max_grid][8][17] per-block 288-bit sums of the factored cipher round
+    uint32_t* partials_w = nullptr;  // 8 x 17 64-bit limb-column sums of the factored cipher round (zero between launches)
     int max_grid = 0;
 
     // pinned, device-mapped result slot
@@ -394,6 +394,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     c->d_all = p; p += 8 * 64;
     c->d_resid = p; p += 3 * 32;
     c->partials_w = (uint32_t*)p; p += ((size_t)c->n_sm * 8 * 8 * 17 * 4 + 31) / 32;
+    CUDA_TRY(cudaMemset(c->partials_w, 0, 8 * 17 * 8));
     CUDA_TRY(cudaMalloc(&c->ticket, 64));
     CUDA_TRY(cudaMemset(c->ticket, 0, 64));
     CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 512 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
@@ -928,7 +929,9 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         const int grid = grid_for(par8 ? half * 8 : half, blk, n_sm * (par8 ? CF_MINB8 : cf_blocks_per_sm1[nm - 7]));  // at most one resident wave
         LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, blk, cf_smem(nm, par8), a);
         CUDA_TRY(cudaGetLastError());
-        st.fr_mul_round += (uint64_t)half * ((nm == 8 ? 20 : 18) + (mk > c ? 1 : 0) + (do_fold ? 4 : 0));
+        // algorithmic multiplier work in units of one Montgomery product (136 wide multiply-adds): 9 (NM = 8: 11) full products,
+        // NM plain 512-bit products of 64 multiply-adds each, the eq factor product and four folds
+        st.fr_mul_round += (uint64_t)half * (136 * ((nm == 8 ? 11 : 9) + (mk > c ? 1 : 0) + (do_fold ? 4 : 0)) + 64 * nm) / 136;
         st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
         if (do_fold) {
             cur[0] = dstp[0];

@@ -446,7 +446,7 @@ __device__ __forceinline__ void widen_add(uint32_t (&a)[WL], const uint32_t (&b)
 }
 
 struct WideOut {
-    uint32_t* partials;            // [gridDim.x][NM][WL] device scratch
+    uint32_t* partials;            // NM x WL 64-bit column sums (device scratch, zero between launches)
     unsigned int* ticket;          // device counter, zero between launches
     unsigned long long* result;    // NM x 9 words, each (seq << 32) | limb of a 288-bit plain sum (NOT reduced mod q);
                                    // device memory or mapped host memory
@@ -478,7 +478,7 @@ __device__ __forceinline__ void publish_word(unsigned long long* dst, uint32_t s
 }
 
 // Grid stage shared by both layouts of k_round_cf.  tot: this block's NM x 9 limb sums in shared memory
-// (tot[k*9 + l]); scratch: >= (BLOCK/8) * NM * 9 words of shared memory.  No field multiplication anywhere:
+// (tot[k*WL + l]); scratch: >= 2 * NM * WL words of shared memory.  No field multiplication anywhere:
 // the host reduces the NM wide sums modulo q.
 template <int NM, int WL, int BLOCK>
 __device__ __forceinline__ void grid_stage_wide(const uint32_t* tot, uint32_t* scratch, const WideOut& out) {
@@ -490,46 +490,33 @@ __device__ __forceinline__ void grid_stage_wide(const uint32_t* tot, uint32_t* s
         GKR_T(6);
         return;
     }
-    for (int i = tid; i < NM * WL; i += BLOCK) out.partials[(size_t)blockIdx.x * (NM * WL) + i] = tot[i];
+    // Every block adds its NM x WL limbs to 64-bit COLUMN sums in global memory (RED.ADD.64, fire and forget: a column
+    // holds < gridDim.x * 2^32, no carries between columns yet); the last block to arrive propagates the carries once.
+    // The earlier scheme (per-block partials summed by the last block) cost ~20 us per 444-block launch: one SM
+    // walking 200 KB of partials at L2 latency.
+    unsigned long long* gacc = reinterpret_cast<unsigned long long*>(out.partials);
+    for (int i = tid; i < NM * WL; i += BLOCK) atomicAdd(gacc + i, (unsigned long long)tot[i]);
     __threadfence();
     __syncthreads();
     if (tid == 0) is_last_r = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!is_last_r) return;
     __threadfence();
-    // last block: lane group (tid >> 3) sums the partials of blocks tid>>3, +BLOCK/8, ... for accumulator tid & 7
-    {
-        const int k = tid & 7, slice = tid >> 3;
-        uint32_t a[WL];
-#pragma unroll
-        for (int l = 0; l < WL; l++) a[l] = 0;
-        if (k < NM) {
-#pragma unroll 1
-            for (unsigned b = slice; b < gridDim.x; b += BLOCK / 8) {
-                const uint32_t* pp = out.partials + (size_t)b * (NM * WL) + k * WL;
-                uint32_t w[WL];
-#pragma unroll
-                for (int l = 0; l < WL; l++) w[l] = __ldcg(pp + l);
-                widen_add<WL>(a, w);
-            }
-#pragma unroll
-            for (int l = 0; l < WL; l++) scratch[(slice * NM + k) * WL + l] = a[l];
-        }
+    for (int i = tid; i < NM * WL; i += BLOCK) {
+        const unsigned long long v = __ldcg(gacc + i);
+        gacc[i] = 0;  // ready for the next launch on this stream
+        scratch[i] = (uint32_t)v;
+        scratch[NM * WL + i] = (uint32_t)(v >> 32);
     }
     __syncthreads();
     if (tid < NM) {
-        uint32_t a[WL];
+        unsigned long long carry = 0;
 #pragma unroll
-        for (int l = 0; l < WL; l++) a[l] = scratch[tid * WL + l];
-#pragma unroll 1
-        for (int sl = 1; sl < BLOCK / 8; sl++) {
-            uint32_t w[WL];
-#pragma unroll
-            for (int l = 0; l < WL; l++) w[l] = scratch[(sl * NM + tid) * WL + l];
-            widen_add<WL>(a, w);
+        for (int l = 0; l < WL; l++) {
+            const unsigned long long v = ((unsigned long long)scratch[NM * WL + tid * WL + l] << 32 | scratch[tid * WL + l]) + carry;
+            publish_word(out.result + tid * WL + l, out.seq, (uint32_t)v);
+            carry = v >> 32;
         }
-#pragma unroll
-        for (int l = 0; l < WL; l++) publish_word(out.result + tid * WL + l, out.seq, a[l]);
     }
     if (tid == 0) *out.ticket = 0;
     GKR_T(6);
@@ -652,21 +639,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
                 bv = fr_add(fr_sub(t0, b0), fr_sub(t1, b1));      // (top + ark) - (bottom + ark)
             }
             Fr u = a.tA ? fr_mulc(fr_load(a.tA + (x >> a.c)), fr_load(a.tB + (x & cmask))) : fr_load(a.tB + x);
-            Fr bp[NM];  // bp[i] = b^i, i >= 1
-            bp[1] = bv;
-            bp[2] = fr_sqrc(bv);
-            bp[3] = fr_mulc(bp[2], bv);
-            bp[4] = fr_sqrc(bp[2]);
-            bp[5] = fr_mulc(bp[4], bv);
-            bp[6] = fr_sqrc(bp[3]);
-            // the NM products that only feed the sums are accumulated UNREDUCED (fr_mul_acc_wide): m_i += (T a^(7-i)) * b^i
-            if (NM == 8) fr_mul_acc_wide(sm + (size_t)7 * WL1 * BLOCK + tid, BLOCK, u, fr_mulc(bp[6], bv));
-#pragma unroll
-            for (int i = 6; i >= 1; i--) {
-                u = fr_mulc(u, av);  // T * a^(7-i)
-                fr_mul_acc_wide(sm + (size_t)i * WL1 * BLOCK + tid, BLOCK, u, bp[i]);
+            // m_i = T a^(7-i) b^i as (T * degree-4 monomial) * (degree-3 monomial): the four cubic monomials (6 products),
+            // T a, T a^4 and T a b^3 (3 products) give all of m_0..m_6 as products that only feed the sums, and those are
+            // accumulated UNREDUCED (fr_mul_acc_wide).  9 Montgomery products per pair instead of 11 for powers + chain.
+            Fr v30, v21, v12, v03;
+            {
+                const Fr a2 = fr_sqrc(av), b2 = fr_sqrc(bv);
+                v30 = fr_mulc(a2, av);
+                v21 = fr_mulc(a2, bv);
+                v12 = fr_mulc(av, b2);
+                v03 = fr_mulc(b2, bv);
             }
-            fr_mul_acc_wide(sm + tid, BLOCK, u, av);  // m_0 += (T a^6) * a
+            if (NM == 8) {  // m_7 = (T b * b^3) * b^3
+                const Fr tb4 = fr_mulc(fr_mulc(u, bv), v03);
+                fr_mul_acc_wide(sm + (size_t)7 * WL1 * BLOCK + tid, BLOCK, tb4, v03);
+            }
+            u = fr_mulc(u, av);  // T a
+            {
+                const Fr u1 = fr_mulc(u, v03);  // T a b^3
+                fr_mul_acc_wide(sm + (size_t)4 * WL1 * BLOCK + tid, BLOCK, u1, v21);
+                fr_mul_acc_wide(sm + (size_t)5 * WL1 * BLOCK + tid, BLOCK, u1, v12);
+                fr_mul_acc_wide(sm + (size_t)6 * WL1 * BLOCK + tid, BLOCK, u1, v03);
+            }
+            u = fr_mulc(u, v30);  // T a^4
+            fr_mul_acc_wide(sm + (size_t)3 * WL1 * BLOCK + tid, BLOCK, u, v03);
+            fr_mul_acc_wide(sm + (size_t)2 * WL1 * BLOCK + tid, BLOCK, u, v12);
+            fr_mul_acc_wide(sm + (size_t)1 * WL1 * BLOCK + tid, BLOCK, u, v21);
+            fr_mul_acc_wide(sm + tid, BLOCK, u, v30);
         }
     } else {
         const int j = tid & 7;

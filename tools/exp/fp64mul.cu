@@ -52,8 +52,8 @@ __device__ __forceinline__ FrD mul52(const FrD& a, const FrD& b, const double (&
             ull hp = 0;
 #pragma unroll
             for (int j = 0; j < 5; j++) {
-                const double hi = __fma_rz(md, q[j], C1);
-                const double lo = __fma_rz(md, q[j], C2 - hi);
+                const double hi = __fma_rz(md, c_qd[j], C1);
+                const double lo = __fma_rz(md, c_qd[j], C2 - hi);
                 acc[i + j] = acc[i + j] + (ull)__double_as_longlong(lo) + hp;
                 hp = (ull)__double_as_longlong(hi);
             }
