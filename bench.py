@@ -147,6 +147,7 @@ def workload_config(args, world, P=1, replicas=False):
             "batch sharded on low address bits over %d GPUs, NCCL all-gather of the round polynomials, %d proofs in flight" % (world, P)),
         "l2": "inputs larger than L2: 93 layer tables of %d MiB each per proof" % ((32 << args.bn) >> 20),
         "seeds": [args.seed, args.seed + 1, args.seed + 2],
+        **({"options": args.opt} if args.opt else {}),
     }
 
 
@@ -165,6 +166,7 @@ def main():
     ap.add_argument("--mode", default="sharded", choices=["sharded", "replicas"],
                     help="N > 1 GPUs: 'sharded' = every 2^bn batch is split over all N GPUs (one proof, round sums exchanged; the north-star "
                          "configuration, strong scaling); 'replicas' = every GPU proves its own 2^bn batches (no exchange, weak scaling)")
+    ap.add_argument("--opt", action="append", default=[], metavar="ID=VALUE", help="gkrb200_set_option passthrough (tuning experiments), repeatable")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -223,6 +225,10 @@ def main():
     torch.cuda.set_stream(main_stream)
     ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream) for st_ in streams]
     ctx = ctxs[0]
+    for kv in args.opt:
+        oid, val = kv.split("=")
+        for c in ctxs:
+            c.set_option(int(oid), int(val))
     if sharded:
         for c in ctxs:  # one communicator per pipeline, created in the same order on every rank
             uid = [gkrb200.Context.comm_unique_id() if rank == 0 else None]

@@ -117,6 +117,7 @@ struct gkrb200_ctx {
     FrRaw* d_all = nullptr;      // [8*64]
     FrRaw* d_resid = nullptr;    // [3][TAIL_MAX] residual tables after the last device fold
     int cf_blocks_per_sm1[2] = {CF_MINB1_FWD, CF_MINB1_FWD};
+    int cf_blocks_cap = 0;           // option: cap on the above (0 = none)
     uint32_t* partials_w = nullptr;  // 8 x 17 64-bit limb-column sums of the factored cipher round (zero between launches)
     int max_grid = 0;
 
@@ -926,7 +927,9 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         a.red.result = W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result;
         a.red.seq = seq;
         const int blk = par8 ? CF_BLOCK : CF_BLOCK1;
-        const int grid = grid_for(par8 ? half * 8 : half, blk, n_sm * (par8 ? CF_MINB8 : cf_blocks_per_sm1[nm - 7]));  // at most one resident wave
+        int bps1 = cf_blocks_per_sm1[nm - 7];
+        if (cf_blocks_cap > 0 && bps1 > cf_blocks_cap) bps1 = cf_blocks_cap;
+        const int grid = grid_for(par8 ? half * 8 : half, blk, n_sm * (par8 ? CF_MINB8 : bps1));  // at most one resident wave
         LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, blk, cf_smem(nm, par8), a);
         CUDA_TRY(cudaGetLastError());
         // algorithmic multiplier work in units of one Montgomery product (136 wide multiply-adds): 9 (NM = 8: 11) full products,
@@ -1431,6 +1434,10 @@ extern "C" int gkrb200_set_option(gkrb200_ctx* c, int option, long value) {
         case GKRB200_OPT_PAR8_MAX_PAIRS:
             if (value < 0) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
             c->par8_max_pairs = (size_t)value;
+            return 0;
+        case GKRB200_OPT_CF_BLOCKS_PER_SM:
+            if (value < 0 || value > 32) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
+            c->cf_blocks_cap = (int)value;
             return 0;
         default: return fail(GKRB200_ERR_ARG, "unknown option %d", option);
     }

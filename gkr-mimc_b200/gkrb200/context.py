@@ -69,7 +69,7 @@ class Context:
     def set_profiling(self, on):
         check(lib().gkrb200_set_profiling(self._h, 1 if on else 0))
 
-    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN = 1, 2, 3
+    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN, OPT_CF_BLOCKS_PER_SM = 1, 2, 3, 4
 
     def set_option(self, option, value):
         check(lib().gkrb200_set_option(self._h, option, int(value)))

@@ -167,6 +167,9 @@ int gkrb200_set_profiling(gkrb200_ctx *ctx, int on);
 /* GKRB200_OPT_HOST_TAIL_LEN (power of two, 1..32, default 32): once the tables of a sumcheck have at most this many
  * entries (over all ranks) the remaining rounds run on the host -- a device round trip costs more than they do.   */
 #define GKRB200_OPT_HOST_TAIL_LEN 3
+/* GKRB200_OPT_CF_BLOCKS_PER_SM (>= 1; 0 = as many as fit): cap on the resident blocks per SM the one-wave grid of the
+ * factored round kernel is sized for (occupancy experiments).                               */
+#define GKRB200_OPT_CF_BLOCKS_PER_SM 4
 int gkrb200_set_option(gkrb200_ctx *ctx, int option, long value);
 
 /* integer-pipe microbenchmarks for the roofline denominator: returns achieved rate.
