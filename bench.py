@@ -138,13 +138,15 @@ NCU_TRAFFIC = {22: 272.7e6}
 NCU_TRAFFIC_NOTE = "ncu capture of the round-0 launch of one layer (2^21 pairs: 268.4 MB algorithmic); `achieved` averages all 1564 launches of a proof"
 
 
-def workload_config(args, world, P=1, replicas=False):
+def workload_config(args, world, P=1, replicas=False, exchange=None):
+    xdesc = {"window": "round sums published by the round kernels into a host-shared mapped window read by every rank (no collective on the round path)",
+             "nccl": "NCCL all-gather of the round sums"}.get(exchange, "round sums exchanged every round")
     return {
         "workload": "full MiMC GKR proof (Circuit.Assign + gkr.Prove, 94 layers, transcript bit-exact) of a 2^%d-hash batch over BN254 Fr" % args.bn,
         "bn": args.bn, "hashes_per_step": (1 << args.bn) * (world if replicas else 1), "proof_elements": 1006 * args.bn + 183,
         "parallelism": "single GPU, %d proofs in flight" % P if world == 1 else (
             "replicas: each of the %d GPUs proves its own 2^%d batches, no exchange, %d proofs in flight per GPU" % (world, args.bn, P) if replicas else
-            "batch sharded on low address bits over %d GPUs, NCCL all-gather of the round polynomials, %d proofs in flight" % (world, P)),
+            "batch sharded on low address bits over %d GPUs, %s, %d proofs in flight" % (world, xdesc, P)),
         "l2": "inputs larger than L2: 93 layer tables of %d MiB each per proof" % ((32 << args.bn) >> 20),
         "seeds": [args.seed, args.seed + 1, args.seed + 2],
         **({"options": args.opt} if args.opt else {}),
@@ -225,15 +227,15 @@ def main():
     torch.cuda.set_stream(main_stream)
     ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream) for st_ in streams]
     ctx = ctxs[0]
-    for kv in args.opt:
-        oid, val = kv.split("=")
-        for c in ctxs:
-            c.set_option(int(oid), int(val))
     if sharded:
         for c in ctxs:  # one communicator per pipeline, created in the same order on every rank
             uid = [gkrb200.Context.comm_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             c.comm_init(rank, world, uid[0])
+    for kv in args.opt:  # after comm_init: GKRB200_OPT_EXCHANGE refers to the communicator
+        oid, val = kv.split("=")
+        for c in ctxs:
+            c.set_option(int(oid), int(val))
     circuits = [gkrb200.MimcCircuit(c) for c in ctxs]
 
     # synthetic inputs: pinned host copies (e2e path) and device-resident copies (kernel path)
@@ -361,7 +363,7 @@ def main():
         line = {
             "metric": METRIC, "value": n_step / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if replicas else "strong", "vs_baseline": None, "dtype": "u32x8 (BN254 Fr, Montgomery)",
-            "data": "synthetic", "config": workload_config(args, world, P, replicas), "clocks": clocks,
+            "data": "synthetic", "config": workload_config(args, world, P, replicas, ctx.exchange_mode), "clocks": clocks,
             "e2e": {"value": n_step / (ms_e2e / args.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),

@@ -8,7 +8,11 @@
 // The device does all O(N) work; the host keeps only the O(bn) serial transcript.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
 #include <nccl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -135,6 +139,21 @@ struct gkrb200_ctx {
     // multi-GPU
     int rank = 0, world = 1, log_world = 0;
     ncclComm_t comm = nullptr;
+    // Exchange window: one POSIX shared-memory segment per communicator, mapped by every rank of the box and registered
+    // with CUDA as mapped pinned memory.  Rank g's kernels publish their round sums straight into slot [parity][g]
+    // (the same tagged stores they use for the single-GPU result slot) and every rank's host thread reads all slots:
+    // the per-round "all-reduce" of a few hundred bytes costs no collective, no extra launch and no device-side wait.
+    // Two parities: a rank can run at most one exchange ahead of the slowest reader (it needs that reader's next
+    // contribution before it can publish again).
+    uint8_t* x_base = nullptr;  // host mapping
+    uint8_t* x_dev = nullptr;   // device alias
+    size_t x_size = 0;
+    uint32_t xseq = 0;          // tag of the last exchange (identical on every rank: all ranks run the same exchanges)
+    bool use_window = false;    // false: NCCL all-gather + publish kernel (GKRB200_OPT_EXCHANGE = 1, or no usable /dev/shm)
+    static constexpr size_t XSLOT_DATA = 16384, XSLOT = XSLOT_DATA + 64;
+    uint8_t* xslot_h(uint32_t tag, int g) const { return x_base + ((size_t)(tag & 1) * (size_t)world + (size_t)g) * XSLOT; }
+    uint8_t* xslot_d(uint32_t tag, int g) const { return x_dev + ((size_t)(tag & 1) * (size_t)world + (size_t)g) * XSLOT; }
+    bool windowed(int W) const { return W > 1 && use_window; }
 
     // instrumentation
     gkrb200_stats st{};
@@ -158,7 +177,9 @@ struct gkrb200_ctx {
     void prof_begin(int cls);
     void prof_end();
     int wait_flag(uint32_t seq);
+    int wait_flag_at(const volatile uint32_t* flag, uint32_t seq);
     int wait_words(uint32_t seq, size_t n_words);
+    int wait_words_at(const volatile uint64_t* w, uint32_t seq, size_t n_words);
     int upload(FrRaw* dst, const void* src, size_t n_elems);
 
     int build_eq(const H::Fr* qprimes, size_t n_q, int bn_local, const H::Fr* mults, FrRaw* out);
@@ -167,8 +188,8 @@ struct gkrb200_ctx {
                  const H::Fr* trusted_claim = nullptr);
     size_t par8_max_pairs = 8192;  // rounds with at most this many pairs spread one pair over 8 lanes
     bool force_generic = false;  // test hook: run cipher layers through the generic evaluate-at-9-points kernel
-    int exchange_and_fetch(int nacc, H::Fr* out);
-    int exchange_and_fetch_wide(int nm, int wl, H::Fr* out);
+    int exchange_and_fetch(int nacc, int W, uint32_t tag, H::Fr* out);
+    int exchange_and_fetch_wide(int nm, int wl, int W, uint32_t tag, H::Fr* out);
     int mle_eval(const FrRaw* table, int bn_total, const H::Fr* point, bool use_shards, H::Fr* out);
     int fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX_FWD]);
     int tail_len = TAIL_MAX_FWD;     // option: residual length (entries over all ranks) handed to the host
@@ -219,7 +240,8 @@ int gkrb200_ctx::ev_flush() {
     } while (0)
 
 // spin on the mapped flag; bail out if the stream died or after a generous timeout (never hang the box)
-int gkrb200_ctx::wait_flag(uint32_t want) {
+int gkrb200_ctx::wait_flag(uint32_t want) { return wait_flag_at(h_flag, want); }
+int gkrb200_ctx::wait_flag_at(const volatile uint32_t* h_flag, uint32_t want) {
     const double t0 = now_ms();
     unsigned spins = 0;
     while (*h_flag != want) {
@@ -227,8 +249,8 @@ int gkrb200_ctx::wait_flag(uint32_t want) {
         if ((++spins & 0xfff) == 0) {
             cudaError_t q = cudaStreamQuery(stream);
             if (q != cudaSuccess && q != cudaErrorNotReady) return fail(GKRB200_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(q));
-            if (q == cudaSuccess && *h_flag != want) {
-                // stream drained: give the write a moment to land, then give up
+            if (q == cudaSuccess && *h_flag != want && h_flag == this->h_flag) {
+                // own result slot and the stream drained: give the write a moment to land, then give up
                 for (int i = 0; i < 100000 && *h_flag != want; i++) _mm_pause();
                 if (*h_flag != want) return fail(GKRB200_ERR_CUDA, "device finished without publishing result %u (have %u)", want, *h_flag);
             }
@@ -241,9 +263,9 @@ int gkrb200_ctx::wait_flag(uint32_t want) {
 }
 
 // spin until every tagged 64-bit word of h_result carries `want` in its upper half (see publish_word in kernels.cuh)
-int gkrb200_ctx::wait_words(uint32_t want, size_t n_words) {
+int gkrb200_ctx::wait_words(uint32_t want, size_t n_words) { return wait_words_at((const volatile uint64_t*)h_result, want, n_words); }
+int gkrb200_ctx::wait_words_at(const volatile uint64_t* w, uint32_t want, size_t n_words) {
     const double t0 = now_ms();
-    const volatile uint64_t* w = (const volatile uint64_t*)h_result;
     unsigned spins = 0;
     for (;;) {
         bool all = true;
@@ -424,6 +446,10 @@ extern "C" void gkrb200_free(gkrb200_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    if (c->x_base) {
+        cudaHostUnregister(c->x_base);
+        munmap(c->x_base, c->x_size);
+    }
     for (auto& e : c->ev_pool) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -455,9 +481,68 @@ extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint
     CUDA_TRY(cudaSetDevice(c->device));
     ncclUniqueId id;
     memcpy(id.internal, uid, 128);
+    // ---- exchange window (see gkrb200_ctx): opened by every rank BEFORE the NCCL rendezvous, unlinked by rank 0 after it
+    char name[64];
+    {
+        uint64_t h = 1469598103934665603ull;  // FNV-1a of the unique id: every communicator gets its own segment
+        for (int i = 0; i < 128; i++) h = (h ^ uid[i]) * 1099511628211ull;
+        snprintf(name, sizeof name, "/gkrb200-%016llx", (unsigned long long)h);
+    }
+    const size_t xsize = 2 * (size_t)world * gkrb200_ctx::XSLOT;
+    int fd = -1;
+    if (rank == 0) {
+        shm_unlink(name);
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd >= 0 && ftruncate(fd, (off_t)xsize) != 0) {  // ftruncate zero-fills: tag 0 is never used by an exchange
+            close(fd);
+            fd = -1;
+        }
+    }
+    // NCCL's rendezvous doubles as the barrier "rank 0 has created the segment"
     NCCL_TRY(g_nccl.CommInitRank(&c->comm, world, id, rank));
+    if (rank != 0) {
+        fd = shm_open(name, O_RDWR, 0600);
+        struct stat sb;
+        if (fd >= 0 && (fstat(fd, &sb) != 0 || (size_t)sb.st_size != xsize)) {
+            close(fd);
+            fd = -1;
+        }
+    }
+    uint8_t ok = 0;
+    void* base = MAP_FAILED;
+    if (fd >= 0) {
+        base = mmap(nullptr, xsize, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        close(fd);
+        if (base != MAP_FAILED) {
+            void* dev = nullptr;
+            if (cudaHostRegister(base, xsize, cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess &&
+                cudaHostGetDevicePointer(&dev, base, 0) == cudaSuccess && dev) {
+                c->x_base = (uint8_t*)base;
+                c->x_dev = (uint8_t*)dev;
+                c->x_size = xsize;
+                ok = 1;
+            } else {
+                cudaGetLastError();
+                munmap(base, xsize);
+            }
+        }
+    }
+    // all ranks must agree on the exchange path: gather everybody's verdict (this is also the barrier before the unlink)
+    CUDA_TRY(cudaMemcpyAsync(c->d_local, &ok, 1, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(g_nccl.AllGather(c->d_local, c->d_all, 1, ncclUint8, c->comm, c->stream));
+    uint8_t oks[8] = {0};
+    CUDA_TRY(cudaMemcpyAsync(oks, c->d_all, (size_t)world, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (rank == 0) shm_unlink(name);
+    bool all_ok = true;
+    for (int g = 0; g < world; g++) all_ok = all_ok && oks[g] == 1;
+    c->use_window = all_ok;
+    c->xseq = 0;
+    if (!all_ok && getenv("GKRB200_VERBOSE")) fprintf(stderr, "gkrb200: rank %d: no shared exchange window (ok=%d), using NCCL all-gather\n", rank, (int)ok);
     return 0;
 }
+
+extern "C" int gkrb200_comm_exchange_mode(gkrb200_ctx* c) { return (!c || c->world <= 1) ? -1 : (c->use_window ? 0 : 1); }
 
 // ------------------------------------------------------------------------------------------------ K1 assign
 static int assign_common(gkrb200_ctx* c, size_t n_local) {
@@ -562,18 +647,29 @@ int gkrb200_ctx::build_eq(const H::Fr* qprimes, size_t n_q, int bnl, const H::Fr
 }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU exchange
-// Single GPU: the kernel already published into h_result.  Sharded: all-gather the per-rank partials over
-// NCCL/NVLink, sum them modulo q on the device and publish.  Then wait and copy `nacc` elements to out.
-int gkrb200_ctx::exchange_and_fetch(int nacc, H::Fr* out) {
-    if (eff_world() > 1) {
+// Single GPU: the kernel already published into h_result.  Sharded, exchange window (default): every rank's kernel
+// published its partial sums + flag into its own slot of the window; wait for all W flags and add.  Sharded, NCCL
+// (GKRB200_OPT_EXCHANGE = 1): all-gather the per-rank partials over NVLink, sum them on the device and publish.
+int gkrb200_ctx::exchange_and_fetch(int nacc, int W, uint32_t tag, H::Fr* out) {
+    if (windowed(W)) {
+        for (int g = 0; g < W; g++) TRY(wait_flag_at((const volatile uint32_t*)(xslot_h(tag, g) + XSLOT_DATA), tag));
+        for (int k = 0; k < nacc; k++) {
+            H::Fr s = ((const H::Fr*)xslot_h(tag, 0))[k];
+            for (int g = 1; g < W; g++) s = H::add(s, ((const H::Fr*)xslot_h(tag, g))[k]);
+            out[k] = s;
+        }
+        st.d2h_bytes += ((size_t)nacc * sizeof(H::Fr) + 4) * (size_t)W;
+        return 0;
+    }
+    if (W > 1) {
         const double t0 = now_ms();
         NCCL_TRY(g_nccl.AllGather(d_local, d_all, (size_t)nacc * sizeof(FrRaw), ncclUint8, comm, stream));
         st.launches_total++;
         st.launches[KC_MISC]++;
-        gkr::k_sum_ranks<<<1, 32, 0, stream>>>(d_all, world, nacc, h_result, h_flag, seq);
+        gkr::k_sum_ranks<<<1, 32, 0, stream>>>(d_all, world, nacc, h_result, h_flag, tag);
         st.comm_ms += now_ms() - t0;
     }
-    TRY(wait_flag(seq));
+    TRY(wait_flag(tag));
     memcpy(out, (const void*)h_result, (size_t)nacc * sizeof(H::Fr));
     st.d2h_bytes += (size_t)nacc * sizeof(H::Fr) + 4;
     return 0;
@@ -672,6 +768,26 @@ int gkrb200_ctx::fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, 
             CUDA_TRY(cudaMemcpyAsync(d_resid + (size_t)i * lres, cur[i], lres * sizeof(FrRaw), cudaMemcpyDeviceToDevice, stream));
     }
     const size_t per_rank = (size_t)ntab * lres;
+    if (windowed(W)) {
+        // every rank publishes its residual entries (tagged 32-bit limbs) into its slot of the exchange window
+        const uint32_t tag = ++xseq;
+        const int n_limbs = (int)(per_rank * 8);
+        LAUNCH(this, KC_MISC, gkr::k_publish_tagged, 1, 256, 0, (const uint32_t*)d_resid, n_limbs, (unsigned long long*)xslot_d(tag, rank), tag);
+        CUDA_TRY(cudaGetLastError());
+        for (int g = 0; g < W; g++) TRY(wait_words_at((const volatile uint64_t*)xslot_h(tag, g), tag, (size_t)n_limbs));
+        st.d2h_bytes += per_rank * (size_t)W * sizeof(FrRaw);
+        for (int g = 0; g < W; g++) {
+            const volatile uint64_t* w = (const volatile uint64_t*)xslot_h(tag, g);
+            for (int t = 0; t < ntab; t++)
+                for (size_t j = 0; j < lres; j++) {
+                    const volatile uint64_t* e = w + ((size_t)t * lres + j) * 8;
+                    H::Fr v;
+                    for (int l = 0; l < 4; l++) v.l[l] = (uint64_t)(uint32_t)e[2 * l] | ((uint64_t)(uint32_t)e[2 * l + 1] << 32);
+                    tabs[t][j * (size_t)W + g] = v;
+                }
+        }
+        return 0;
+    }
     const FrRaw* src = d_resid;
     if (W > 1) {
         const double t0 = now_ms();
@@ -755,7 +871,6 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
     FrRaw* dstp[3] = {scratch[0], scratch[1], scratch[2]};
     size_t len = n_local;
     H::Fr evals[MAX_EV], r = H::zero();
-    FrRaw* result_dev = W > 1 ? d_local : h_result;
     // the last rounds (residual table of at most tail_len entries over all ranks) are finished on the host
     int tail_bits = 0;
     while (((size_t)2 << tail_bits) * (size_t)W <= (size_t)tail_len && tail_bits < bnl) tail_bits++;
@@ -771,12 +886,12 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         a.half = half;
         memcpy(&a.r, &r, 32);
         memcpy(&a.ark, &ark, 32);
-        ++seq;
+        const uint32_t tag = windowed(W) ? ++xseq : ++seq;
         a.red.partials = partials;
         a.red.ticket = ticket;
-        a.red.result = result_dev;
-        a.red.flag = W > 1 ? nullptr : h_flag;
-        a.red.seq = seq;
+        a.red.result = windowed(W) ? (FrRaw*)xslot_d(tag, rank) : (W > 1 ? d_local : h_result);
+        a.red.flag = windowed(W) ? (volatile uint32_t*)(xslot_d(tag, rank) + XSLOT_DATA) : (W > 1 ? nullptr : h_flag);
+        a.red.seq = tag;
         const int grid = grid_for(half, ROUND_BLOCK, max_grid);
         const size_t smem = (size_t)nev * 9 * ROUND_BLOCK * 4;
         if (gate == gkr::GATE_CIPHER) {
@@ -795,7 +910,7 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
             for (int i = 0; i < 3; i++) cur[i] = dstp[i];
             len /= 2;
         }
-        TRY(exchange_and_fetch(nev, evals));
+        TRY(exchange_and_fetch(nev, W, tag, evals));
         const double t0 = now_ms();
         H::Fr* coeffs = proof_out + (size_t)k * nev;
         lagrange.interpolate(evals, nev, coeffs);  // poly/lagrange.go:96
@@ -811,21 +926,27 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
     return 0;
 }
 
-// Wide variant for the factored cipher round: nm 288-bit sums per rank.
-int gkrb200_ctx::exchange_and_fetch_wide(int nm, int wl, H::Fr* out) {
-    const int W = eff_world();
+// Wide variant for the factored cipher round: nm 288- or 544-bit sums per rank, as tagged words.
+int gkrb200_ctx::exchange_and_fetch_wide(int nm, int wl, int W, uint32_t tag, H::Fr* out) {
     const size_t words = (size_t)nm * wl;
-    if (W > 1) {
-        const double t0 = now_ms();
-        NCCL_TRY(g_nccl.AllGather(d_local, d_all, words * 8, ncclUint8, comm, stream));
-        st.launches_total++;
-        st.launches[KC_MISC]++;
-        gkr::k_publish_words<<<1, 128, 0, stream>>>((const unsigned long long*)d_all, (int)(words * W), (unsigned long long*)h_result);
-        st.comm_ms += now_ms() - t0;
-    }
-    TRY(wait_words(seq, words * (size_t)W));
     const volatile uint64_t* w = (const volatile uint64_t*)h_result;
-    for (int i = 0; i < nm; i++) out[i] = wide_to_fr(w + (size_t)i * wl, wl, W, words);
+    size_t rank_stride = words;
+    if (windowed(W)) {
+        for (int g = 0; g < W; g++) TRY(wait_words_at((const volatile uint64_t*)xslot_h(tag, g), tag, words));
+        w = (const volatile uint64_t*)xslot_h(tag, 0);
+        rank_stride = XSLOT / 8;
+    } else {
+        if (W > 1) {
+            const double t0 = now_ms();
+            NCCL_TRY(g_nccl.AllGather(d_local, d_all, words * 8, ncclUint8, comm, stream));
+            st.launches_total++;
+            st.launches[KC_MISC]++;
+            gkr::k_publish_words<<<1, 128, 0, stream>>>((const unsigned long long*)d_all, (int)(words * W), (unsigned long long*)h_result);
+            st.comm_ms += now_ms() - t0;
+        }
+        TRY(wait_words(tag, words * (size_t)W));
+    }
+    for (int i = 0; i < nm; i++) out[i] = wide_to_fr(w + (size_t)i * wl, wl, W, rank_stride);
     st.d2h_bytes += words * 8 * (size_t)W;
     return 0;
 }
@@ -921,11 +1042,11 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
             a.tB = lo + ((size_t)1 << mk);
         }
         a.c = c;
-        ++seq;
+        const uint32_t tag = windowed(W) ? ++xseq : ++seq;
         a.red.partials = partials_w;
         a.red.ticket = ticket;
-        a.red.result = W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result;
-        a.red.seq = seq;
+        a.red.result = windowed(W) ? (unsigned long long*)xslot_d(tag, rank) : (W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result);
+        a.red.seq = tag;
         const int blk = par8 ? CF_BLOCK : CF_BLOCK1;
         int bps1 = cf_blocks_per_sm1[nm - 7];
         if (cf_blocks_cap > 0 && bps1 > cf_blocks_cap) bps1 = cf_blocks_cap;
@@ -940,7 +1061,7 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
             cur[0] = dstp[0];
             cur[1] = dstp[1];
         }
-        TRY(exchange_and_fetch_wide(nm, par8 ? CF_WL8 : CF_WL1, m));
+        TRY(exchange_and_fetch_wide(nm, par8 ? CF_WL8 : CF_WL1, W, tag, m));
         const double t0 = now_ms();
         const H::Fr w0 = H::sub(one, q[k]), w1 = H::sub(q[k], w0);  // eq(q_k, t) = w0 + w1*t
         if (nm == 7) {
@@ -1438,6 +1559,11 @@ extern "C" int gkrb200_set_option(gkrb200_ctx* c, int option, long value) {
         case GKRB200_OPT_CF_BLOCKS_PER_SM:
             if (value < 0 || value > 32) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
             c->cf_blocks_cap = (int)value;
+            return 0;
+        case GKRB200_OPT_EXCHANGE:
+            if (value != 0 && value != 1) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
+            if (value == 0 && c->world > 1 && !c->x_base) return fail(GKRB200_ERR_STATE, "this communicator has no exchange window");
+            c->use_window = value == 0 && c->x_base != nullptr;
             return 0;
         default: return fail(GKRB200_ERR_ARG, "unknown option %d", option);
     }

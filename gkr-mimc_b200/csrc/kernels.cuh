@@ -772,6 +772,11 @@ __global__ void k_publish_words(const unsigned long long* __restrict__ src, int 
     }
 }
 
+// tags n 32-bit words with seq and publishes them (residual tables of one rank -> its slot of the exchange window)
+__global__ void k_publish_tagged(const uint32_t* __restrict__ src, int n, unsigned long long* dst, uint32_t seq) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) publish_word(dst + i, seq, src[i]);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Multi-GPU helpers
 // ------------------------------------------------------------------------------------------------

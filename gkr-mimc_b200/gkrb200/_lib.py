@@ -52,6 +52,7 @@ def lib():
     L.gkrb200_free.restype = None
     L.gkrb200_comm_unique_id.argtypes = [vp]
     L.gkrb200_comm_init.argtypes = [vp, i32, i32, vp]
+    L.gkrb200_comm_exchange_mode.argtypes = [vp]
     L.gkrb200_mimc_assign.argtypes = [vp, vp, vp, sz, vp]
     L.gkrb200_mimc_assign_device.argtypes = [vp, vp, vp, sz]
     L.gkrb200_assign_layer_to_host.argtypes = [vp, i32, vp, sz]

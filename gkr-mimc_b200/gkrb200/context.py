@@ -41,6 +41,11 @@ class Context:
         check(lib().gkrb200_comm_init(self._h, rank, world, buf))
         self.rank, self.world = rank, world
 
+    @property
+    def exchange_mode(self):
+        """'window' (round kernels publish into host-shared mapped memory), 'nccl' (all-gather) or None (single GPU)"""
+        return {0: "window", 1: "nccl"}.get(lib().gkrb200_comm_exchange_mode(self._h))
+
     # -- lifetime ----------------------------------------------------------------------------
     def close(self):
         if self._h:
@@ -69,7 +74,7 @@ class Context:
     def set_profiling(self, on):
         check(lib().gkrb200_set_profiling(self._h, 1 if on else 0))
 
-    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN, OPT_CF_BLOCKS_PER_SM = 1, 2, 3, 4
+    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN, OPT_CF_BLOCKS_PER_SM, OPT_EXCHANGE = 1, 2, 3, 4, 5
 
     def set_option(self, option, value):
         check(lib().gkrb200_set_option(self._h, option, int(value)))

@@ -60,6 +60,9 @@ void gkrb200_free(gkrb200_ctx *ctx);
  * ncclUniqueId produced by gkrb200_comm_unique_id on rank 0 and broadcast by the caller.               */
 int gkrb200_comm_unique_id(uint8_t id_out[128]);
 int gkrb200_comm_init(gkrb200_ctx *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
+/* how the per-round partial sums travel between the ranks: 0 = exchange window (host-shared mapped memory written by the
+ * round kernels themselves), 1 = NCCL all-gather, -1 = single GPU (see GKRB200_OPT_EXCHANGE)                       */
+int gkrb200_comm_exchange_mode(gkrb200_ctx *ctx);
 
 /* ---- circuit.Circuit.Assign  (circuit/assignment.go:12-32, circuit/circuit.go:48-64,
  *      circuit/gates/cipher.go:25-42) for examples.MimcCircuit() (examples/mimc.go:10-37) -------------------
@@ -170,6 +173,11 @@ int gkrb200_set_profiling(gkrb200_ctx *ctx, int on);
 /* GKRB200_OPT_CF_BLOCKS_PER_SM (>= 1; 0 = as many as fit): cap on the resident blocks per SM the one-wave grid of the
  * factored round kernel is sized for (occupancy experiments).                               */
 #define GKRB200_OPT_CF_BLOCKS_PER_SM 4
+/* GKRB200_OPT_EXCHANGE (multi-GPU, set identically on every rank): 0 (default) = exchange window -- every rank's round
+ * kernel publishes its partial sums straight into a host-shared mapped segment that all ranks' host threads read (no
+ * collective, no extra launch); 1 = NCCL all-gather of the partials + a publishing kernel (A/B reference; also what
+ * gkrb200_comm_init falls back to, on all ranks together, when /dev/shm cannot be mapped).                          */
+#define GKRB200_OPT_EXCHANGE 5
 int gkrb200_set_option(gkrb200_ctx *ctx, int option, long value);
 
 /* integer-pipe microbenchmarks for the roofline denominator: returns achieved rate.

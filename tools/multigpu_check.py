@@ -18,12 +18,18 @@ dist.broadcast_object_list(uid, src=0)
 ctx.comm_init(rank, world, uid[0])
 c = gkrb200.MimcCircuit(ctx)
 ok = True
-for bn in list(range(0, 9)) + [max_bn]:
+import time
+# every size through the exchange window (default), then again through the NCCL all-gather exchange (A/B)
+for mode, bn in [(0, b) for b in list(range(0, 9)) + [max_bn]] + [(1, b) for b in (2, 3, 5, 8, max_bn)]:
+    if world > 1:
+        ctx.set_option(gkrb200.Context.OPT_EXCHANGE, mode)
     n = 1 << bn
     rng = np.random.default_rng(100 + bn)
     key = gkrb200.common.RandomFrArray(n); msg = key[::-1].copy(); q = gkrb200.common.RandomFrArray(bn + 1)[1:]
     a = c.Assign(key, msg, want_outputs=True)
+    t0 = time.perf_counter()
     vec = gkrb200.gkr.Prove(c, a, q).to_vec()
+    prove_ms = (time.perf_counter() - t0) * 1e3
     out93, evec = coracle.assign_and_prove_mimc(key, msg, q)
     sharded = world > 1 and n > world
     exp_out = out93[rank::world] if sharded else out93
@@ -47,7 +53,8 @@ for bn in list(range(0, 9)) + [max_bn]:
     t = torch.tensor([1 if good else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("bn=%2d world=%d sharded=%s : %s" % (bn, world, sharded, "OK (bit-exact on all ranks)" if t.item() else "MISMATCH"), flush=True)
+        print("bn=%2d world=%d sharded=%s exchange=%s prove=%.1f ms : %s" % (bn, world, sharded, "nccl" if mode else "window", prove_ms,
+                                                                        "OK (bit-exact on all ranks)" if t.item() else "MISMATCH"), flush=True)
     ok = ok and bool(t.item())
 ctx.close()
 dist.destroy_process_group()
