@@ -209,7 +209,7 @@ __device__ __forceinline__ void chain4_cin(uint32_t& c0, uint32_t& c1, uint32_t&
 // P[p] is the accumulator limb at ABSOLUTE position p (weight 2^(32p)) of the accumulator whose
 // 64-bit columns start at even positions; Qd[p] the same for odd-aligned columns.  Row i adds
 // a*b_i*2^(32i) and m_i*q*2^(32i), which zeroes limb i of P+Qd (mod 2^32); its carry rides into the next chain.
-__device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
+__device__ __forceinline__ Fr fr_mul_school(const Fr& a, const Fr& b) {
     uint32_t P[18], Qd[18];
 #pragma unroll
     for (int i = 0; i < 18; i++) P[i] = 0, Qd[i] = 0;
@@ -246,6 +246,27 @@ __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
           "r"(Qd[8]), "r"(Qd[9]), "r"(Qd[10]), "r"(Qd[11]), "r"(Qd[12]), "r"(Qd[13]), "r"(Qd[14]), "r"(Qd[15]));
     return fr_reduce_once(t);
 }
+}  // namespace gkr
+#include "fr_kara.cuh"  // hd_mul_k / hd_mul_wide_k: the Karatsuba form (120 instead of 136 wide multiply-adds)
+namespace gkr {
+// The multiplier every kernel uses: GKR_MUL_KARA = 0 (default) the operand-scanning form above, 1 the Karatsuba form of
+// fr_kara.cuh; GKR_ACC_KARA likewise for the plain 512-bit products of fr_mul_acc_wide.  All forms give the same canonical
+// residues (the parity suite passes with each build).  Measured on B200 (profiles/r1_exp_karatsuba.txt): Karatsuba saves 16 of
+// 136 wide multiply-adds per product but its ~100 extra carry-chain adds -- a third of which ptxas issues as IMAD.X /
+// IMAD.MOV on the same fmaheavy pipe -- make it SLOWER: 60.0 vs 66.4 G Fr-mul/s in isolation, 164 vs 151 ms per 2^22 proof.
+#ifndef GKR_MUL_KARA
+#define GKR_MUL_KARA 0
+#endif
+#ifndef GKR_ACC_KARA
+#define GKR_ACC_KARA 0
+#endif
+__device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
+#if GKR_MUL_KARA
+    return hd_mul_k(a, b);
+#else
+    return fr_mul_school(a, b);
+#endif
+}
 __device__ __forceinline__ Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
 
 // Out-of-line copy of the multiplier (register ABI, no stack: 16 words in, 8 out).  Kernels that issue many
@@ -259,6 +280,21 @@ __device__ __forceinline__ Fr fr_sqrc(const Fr& a) { return fr_mulc(a, a); }
 // Half the multiplier work of fr_mul (64 of its 136 wide multiply-adds); whoever consumes the sum reduces it once
 // (the host, for the round sums: REDC(sum of products) == sum of Montgomery products, exactly).  544 bits hold
 // 2^36 products of values < q.  Out of line for the same reason as fr_mulc.
+#if GKR_ACC_KARA
+__device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr a, const Fr b) {
+    uint32_t P[16];
+    hd_mul_wide_k(a, b, P);  // 48 wide multiply-adds
+    uint32_t w[17];
+#pragma unroll
+    for (int l = 0; l < 17; l++) w[l] = acc[l * stride];
+    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(w[0]) : "r"(P[0]));
+#pragma unroll
+    for (int l = 1; l < 16; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(w[l]) : "r"(P[l]));
+    asm volatile("addc.u32 %0, %0, 0;" : "+r"(w[16]));
+#pragma unroll
+    for (int l = 0; l < 17; l++) acc[l * stride] = w[l];
+}
+#else
 __device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr a, const Fr b) {
     uint32_t P[18], Qd[18];
 #pragma unroll
@@ -286,6 +322,7 @@ __device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr
 #pragma unroll
     for (int l = 0; l < 17; l++) acc[l * stride] = w[l];
 }
+#endif
 
 // x^7 = ((x^2 * x)^2) * x  -- same chain as hash/poseidon.go:129-135 and circuit/gates/cipher.go:37-40
 __device__ __forceinline__ Fr fr_pow7(const Fr& x) {

@@ -1578,17 +1578,19 @@ extern "C" int gkrb200_trace_get(long long* out16) {
 extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, double* rate_out, double* ms_out) {
     // low byte: kind; next byte (optional): warps per SM to allow (occupancy limited through dynamic shared memory)
     const int kind = kind_and_occ & 0xff, warps = (kind_and_occ >> 8) & 0xff;
-    if (!c || !rate_out || iters < 1 || kind < 0 || kind > 3) return fail(GKRB200_ERR_ARG, "bad argument");
+    if (!c || !rate_out || iters < 1 || kind < 0 || kind > 5) return fail(GKRB200_ERR_ARG, "bad argument");  // 4 / 5: kind 1 with the schoolbook / Karatsuba multiplier
     CUDA_TRY(cudaSetDevice(c->device));
     int block = 256, grid = c->n_sm * 8;
     size_t smem = 0;
-    if (warps && (kind == 1 || kind == 3)) {
+    if (warps && (kind == 1 || kind >= 3)) {
         block = 128;                                  // 4 warps per block
         const int blocks_per_sm = warps / 4 > 0 ? warps / 4 : 1;
         smem = (size_t)(220 * 1024) / blocks_per_sm;  // only blocks_per_sm blocks fit in shared memory
         if (smem > 200 * 1024) smem = 200 * 1024;
         grid = c->n_sm * blocks_per_sm * 2;
-        CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     void* d = nullptr;
@@ -1600,7 +1602,9 @@ extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, d
     for (int rep = 0; rep < 4; rep++) {  // first rep is warm-up
         cudaEventRecord(e0, c->stream);
         if (kind == 0) gkr::k_bench_imad_wide<<<grid, block, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
-        else if (kind == 1) gkr::k_bench_fr_mul<<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
+        else if (kind == 1) gkr::k_bench_fr_mul<0><<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
+        else if (kind == 4) gkr::k_bench_fr_mul<1><<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
+        else if (kind == 5) gkr::k_bench_fr_mul<2><<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
         else if (kind == 2) gkr::k_bench_imad_wide_x<<<grid, block, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
         else gkr::k_bench_fr_mul1<<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
         cudaEventRecord(e1, c->stream);

@@ -874,6 +874,11 @@ __global__ void __launch_bounds__(256) k_bench_imad_wide(uint64_t* out, int iter
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
 }
 // kind 1: two independent dependent-chains of fr_mul per thread (what the prover kernels look like)
+template <int MULT>  // 0: the library's multiplier (fr_mul), 1: schoolbook form, 2: Karatsuba form
+__device__ __forceinline__ Fr bench_mul(const Fr& a, const Fr& b) {
+    return MULT == 1 ? fr_mul_school(a, b) : (MULT == 2 ? hd_mul_k(a, b) : fr_mul(a, b));
+}
+template <int MULT>
 __global__ void k_bench_fr_mul(FrRaw* out, int iters, uint32_t seed) {
     extern __shared__ uint32_t sm_dummy[];  // only used to limit occupancy from the host side
     Fr a = fr_one(), b = fr_one();
@@ -884,8 +889,8 @@ __global__ void k_bench_fr_mul(FrRaw* out, int iters, uint32_t seed) {
     Fr c = b, d = a;
 #pragma unroll 1
     for (int i = 0; i < iters; i++) {
-        a = fr_mul(a, b);
-        c = fr_mul(c, d);
+        a = bench_mul<MULT>(a, b);
+        c = bench_mul<MULT>(c, d);
     }
     fr_store(out + (size_t)blockIdx.x * blockDim.x + threadIdx.x, fr_add(a, c));
 }

@@ -6,7 +6,8 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)  # gkr-mimc_b200/
-SO_PATH = os.path.join(ROOT, "libgkrb200.so")
+_VARIANT = os.environ.get("GKRB200_LIB_VARIANT", "")  # "" (product build) | "kara" | "mixed": A/B builds of the multiplier (make variants)
+SO_PATH = os.path.join(ROOT, "libgkrb200%s.so" % ("_" + _VARIANT if _VARIANT else ""))
 
 
 class Stats(ctypes.Structure):
