@@ -640,7 +640,7 @@ int gkrb200_ctx::build_eq(const H::Fr* qprimes, size_t n_q, int bnl, const H::Fr
     const int cls = n_q > 1 ? KC_MULTIEQ : KC_EQ;
     LAUNCH(this, cls, gkr::k_eq_small, (int)(2 * n_q), 256, 0, d_q, bnl, nh, nl, mults ? d_mults : nullptr, hi, lo);
     const int grid = grid_for(n, 256, n_sm * 8);
-    LAUNCH(this, cls, gkr::k_eq_expand, grid, 256, 0, hi, lo, nh, nl, (int)n_q, out, n);
+    LAUNCH(this, cls, gkr::k_eq_expand, grid, gkr::EQX_BLOCK, 0, hi, lo, nh, nl, (int)n_q, out, n);
     CUDA_TRY(cudaGetLastError());
     // the staging buffer is reused by the next call: make sure the copies above are done
     return 0;

@@ -151,18 +151,35 @@ __global__ void __launch_bounds__(256) k_eq_small(const FrRaw* __restrict__ qpri
     }
 }
 // K2/K5 stage 2: out[x] = sum_j hi_j[x >> nl] * lo_j[x & (2^nl-1)]   (one streaming write of the table)
-__global__ void __launch_bounds__(256) k_eq_expand(const FrRaw* __restrict__ hi, const FrRaw* __restrict__ lo, int nh, int nl, int n_claims,
-                                                    FrRaw* __restrict__ out, size_t n) {
+// The 91 products of an entry only feed a sum, so they are taken as PLAIN 512-bit products (64 instead of 136 wide
+// multiply-adds each, fr_mul_acc_wide on a 17-limb accumulator in shared memory) and reduced in groups of five: 5*q^2 <
+// q*2^256 is exactly the input range of one Montgomery reduction (hd_redc), and REDC(sum of products) is the sum of the
+// Montgomery products, so the result is the same canonical element.  91 claims: 7 192 instead of 12 376 wide multiply-adds.
+constexpr int EQX_BLOCK = 256, EQX_GROUP = 5;
+__global__ void __launch_bounds__(EQX_BLOCK) k_eq_expand(const FrRaw* __restrict__ hi, const FrRaw* __restrict__ lo, int nh, int nl, int n_claims,
+                                                         FrRaw* __restrict__ out, size_t n) {
+    __shared__ uint32_t acc[17 * EQX_BLOCK];
     const size_t mask = ((size_t)1 << nl) - 1;
-    for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < n; x += (size_t)gridDim.x * blockDim.x) {
-        Fr acc = fr_mul(fr_load(hi + (x >> nl)), fr_load(lo + (x & mask)));
+    const int tid = threadIdx.x;
+    for (size_t x = (size_t)blockIdx.x * blockDim.x + tid; x < n; x += (size_t)gridDim.x * blockDim.x) {
+        Fr total = fr_zero();
 #pragma unroll 1
-        for (int j = 1; j < n_claims; j++) {
-            const Fr h = fr_load(hi + ((size_t)j << nh) + (x >> nl));
-            const Fr l = fr_load(lo + ((size_t)j << nl) + (x & mask));
-            acc = fr_add(acc, fr_mul(h, l));
+        for (int j0 = 0; j0 < n_claims; j0 += EQX_GROUP) {
+#pragma unroll
+            for (int l = 0; l < 17; l++) acc[l * EQX_BLOCK + tid] = 0;
+            const int j1 = min(j0 + EQX_GROUP, n_claims);
+#pragma unroll 1
+            for (int j = j0; j < j1; j++) {
+                const Fr h = fr_load(hi + ((size_t)j << nh) + (x >> nl));
+                const Fr l = fr_load(lo + ((size_t)j << nl) + (x & mask));
+                fr_mul_acc_wide(acc + tid, EQX_BLOCK, h, l);
+            }
+            uint32_t t[16];
+#pragma unroll
+            for (int l = 0; l < 16; l++) t[l] = acc[l * EQX_BLOCK + tid];  // limb 16 stays zero: 5*q^2 < 2^512
+            total = fr_add(total, hd_redc(t));
         }
-        fr_store(out + x, acc);
+        fr_store(out + x, total);
     }
 }
 
