@@ -297,6 +297,48 @@ def test_gkr_2pow16_full_size_properties(ctx, oracle):
     assert np.array_equal(proof.Claims[2][45], oracle.evaluate(key, proof.QPrimes[2][45]))
 
 
+def fast_fr(seed, n):
+    """n pseudo-random canonical elements without Python big ints (top limb below q's top limb)"""
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64)
+    a[:, :3] |= rng.integers(0, 2, size=(n, 3), dtype=np.uint64) << np.uint64(63)
+    a[:, 3] %= np.uint64(0x30644E72E131A029)
+    return a
+
+
+@pytest.mark.parametrize("bn", [20, 22])
+def test_gkr_full_size_properties(oracle, bn):
+    """BASELINE configs 4/5 (2^20 and 2^22 hashes, all 93 layer tables resident): the proof is deterministic, the CPU oracle's
+    verifier and the device-backed verifier accept it and reject a corrupted one, sampled hash outputs equal the oracle's
+    MimcKeyedPermutation, and the input claims equal the oracle's MLE evaluations of the inputs."""
+    import gkrb200
+    n = 1 << bn
+    big = gkrb200.Context(device=0, max_bn=bn)
+    try:
+        key, msg, qprime = fast_fr(1000 + bn, n), fast_fr(2000 + bn, n), fast_fr(3000 + bn, bn)
+        c = gkrb200.MimcCircuit(big)
+        a = c.Assign(key, msg, want_outputs=True)
+        vec = gkrb200.gkr.Prove(c, a, qprime).to_vec().copy()
+        assert vec.shape[0] == 1006 * bn + 183
+        a2 = c.Assign(key, msg, want_outputs=True)
+        proof2 = gkrb200.gkr.Prove(c, a2, qprime)
+        assert np.array_equal(vec, proof2.to_vec()), "proof is not deterministic"
+        idx = np.array([0, 1, n // 2 - 1, n // 2, n - 2, n - 1, 12345 % n, 777777 % n])
+        for i in idx:
+            assert np.array_equal(a.outputs[i], oracle.mimc_keyed_permutation(msg[i], key[i])), "hash output %d" % i
+        assert oracle.gkr_verify_mimc(vec, key, msg, a.outputs, qprime) == 0, "oracle verifier rejected the proof"
+        gkrb200.gkr.Verify(c, a2, vec, qprime)
+        bad = vec.copy()
+        bad[17, 1] ^= np.uint64(4)
+        assert oracle.gkr_verify_mimc(bad, key, msg, a.outputs, qprime) != 0
+        with pytest.raises(gkrb200.GkrB200Error):
+            gkrb200.gkr.Verify(c, a2, bad, qprime)
+        assert np.array_equal(proof2.Claims[1][0], oracle.evaluate(msg, proof2.QPrimes[1][0]))
+        assert np.array_equal(proof2.Claims[2][90], oracle.evaluate(key, proof2.QPrimes[2][90]))
+    finally:
+        big.close()
+
+
 # ----------------------------------------------------------------------------- factored cipher round (k_round_cf)
 @pytest.mark.parametrize("bn", [1, 2, 3, 5, 8, 11, 14, 16])
 @pytest.mark.parametrize("par8_max", [0, 16, 1 << 20])
