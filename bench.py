@@ -132,8 +132,8 @@ def run_reference(args, rank, world):
     return 0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the largest k_round_cf launches (ncu --set full, profiles/r1_ncu_k_round_cf_v3_bn22.txt):
-# round 0 (2^21 pairs, no fold) 272.7 MB vs 268.4 MB algorithmic; round 1 (2^20 pairs, fold) 377.7 MB vs 402.7 MB algorithmic
+# dram__bytes_read.sum + dram__bytes_write.sum of the largest k_round_cf launches (ncu --set full, profiles/r1_ncu_k_round_cf_final_bn22.txt):
+# round 0 (2^21 pairs, no fold) 272.7 MB (7 sums) / 273.8 MB (8 sums) vs 268.4 MB algorithmic; round 1 (2^20 pairs, fold) 377.2 MB vs 402.7 MB algorithmic
 NCU_TRAFFIC = {22: 272.7e6}
 NCU_TRAFFIC_NOTE = "ncu capture of the round-0 launch of one layer (2^21 pairs: 268.4 MB algorithmic); `achieved` averages all 1564 launches of a proof"
 
@@ -345,7 +345,7 @@ def main():
                 "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC.get(args.bn), "traffic_note": NCU_TRAFFIC_NOTE, "peak_source": peak_src, "launches": k_launches,
                 "avg_launch_us": k_ms * 1e3 / k_launches, "algorithmic_bytes_per_launch": sp.bytes_round / k_launches,
                 "note": "k_round_cf is integer-pipe bound (19-23 Fr-mul per 128-384 B), not HBM bound: see roofline_int"}
-    roofline_int = {"bound": "integer multiply pipe (IMAD.WIDE.U32 on fmaheavy: 32x32->64 multiply-add, half the 32-bit IMAD rate)", "achieved": achieved_mul, "peak": int_peak, "unit": "G Fr-mul/s",
+    roofline_int = {"bound": "integer multiply pipe (IMAD.WIDE.U32 on fmaheavy: 32x32->64 multiply-add, measured at ~0.45x the 32-bit IMAD rate)", "achieved": achieved_mul, "peak": int_peak, "unit": "G Fr-mul/s",
                     "frac": achieved_mul / int_peak if int_peak else None, "imad_wide_gmacs_measured": imad_rate, "macs_per_fr_mul": 136,
                     "fr_mul_microbench_gmuls": frmul_rate, "frac_of_fr_mul_microbench": achieved_mul / frmul_rate if frmul_rate else None,
                     "share_of_step_kernel_time": k_ms / max(sum(sp.kernel_ms), 1e-9)}
