@@ -161,7 +161,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--bn", type=int, default=22, help="log2 of the batch (BASELINE.json quotes the metric on 2^22)")
     ap.add_argument("--ref-bn", type=int, default=16, help="batch of one --impl reference step (bounded sample)")
-    ap.add_argument("--cpu-bn", type=int, default=18, help="batch of the cpu_baseline sample")
+    ap.add_argument("--cpu-bn", type=int, default=20, help="batch of the cpu_baseline sample")
     ap.add_argument("--seed", type=int, default=0x6B6B72)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--inflight", type=int, default=0, help="proofs in flight per GPU (0 = auto: up to 8, bounded by --steps and by the host cores per rank)")
