@@ -1524,6 +1524,63 @@ extern "C" int gkrb200_from_montgomery(const uint64_t* in, size_t n, uint64_t* o
     return 0;
 }
 
+// poly.EvalUnivariate (poly/lagrange.go:31-39), poly.EvalEq (poly/eq.go:19-32), scalar fr.Element methods, sumcheck.Verify
+extern "C" int gkrb200_eval_univariate(const uint64_t* coeffs, size_t n, const uint64_t* x, uint64_t* out) {
+    if (!coeffs || !x || !out || n < 1) return fail(GKRB200_ERR_ARG, "null argument or empty polynomial");
+    std::vector<H::Fr> c(n);
+    memcpy(c.data(), coeffs, n * 32);
+    H::Fr xx;
+    memcpy(&xx, x, 32);
+    const H::Fr r = H::eval_univariate(c.data(), n, xx);
+    memcpy(out, &r, 32);
+    return 0;
+}
+extern "C" int gkrb200_eval_eq(const uint64_t* q, const uint64_t* h, size_t n, uint64_t* out) {
+    if (!out || (n && (!q || !h))) return fail(GKRB200_ERR_ARG, "null argument");
+    std::vector<H::Fr> a(n), b(n);
+    if (n) memcpy(a.data(), q, n * 32), memcpy(b.data(), h, n * 32);
+    const H::Fr r = H::eval_eq(a.data(), b.data(), n);
+    memcpy(out, &r, 32);
+    return 0;
+}
+extern "C" int gkrb200_fr_scalar(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    if (!a || !out || (op <= 2 && !b)) return fail(GKRB200_ERR_ARG, "null argument");
+    H::Fr x, y = H::zero(), r;
+    memcpy(&x, a, 32);
+    if (b) memcpy(&y, b, 32);
+    switch (op) {
+        case 0: r = H::mul(x, y); break;
+        case 1: r = H::add(x, y); break;
+        case 2: r = H::sub(x, y); break;
+        case 3: {  // the cipher S-box x^7 (circuit/gates/cipher.go:51-54)
+            const H::Fr x2 = H::sqr(x);
+            r = H::mul(H::sqr(H::mul(x2, x)), x);
+            break;
+        }
+        case 4: r = H::is_zero(x) ? H::zero() : H::inv(x); break;  // fr.Element.Inverse (0 -> 0)
+        default: return fail(GKRB200_ERR_ARG, "fr_scalar: unknown op %d", op);
+    }
+    memcpy(out, &r, 32);
+    return 0;
+}
+extern "C" int gkrb200_sumcheck_verify(const uint64_t* claims, size_t n_claims, const uint64_t* proof, int bn, int n_coeffs_per_round,
+                                       uint64_t* challenges_out, uint64_t* final_claim_out, uint64_t* recomb_out) {
+    if (!claims || n_claims < 1 || bn < 0 || (bn > 0 && (!proof || !challenges_out)) || !final_claim_out)
+        return fail(GKRB200_ERR_ARG, "null argument or no claim");
+    if (n_coeffs_per_round < 1 || n_coeffs_per_round > H::Lagrange::MAX_DOMAIN) return fail(GKRB200_ERR_ARG, "bad round polynomial length %d", n_coeffs_per_round);
+    std::vector<H::Fr> cl(n_claims), pr((size_t)bn * (size_t)n_coeffs_per_round), ch((size_t)bn + 1);
+    memcpy(cl.data(), claims, n_claims * 32);
+    if (bn) memcpy(pr.data(), proof, pr.size() * 32);
+    H::Fr fin, recomb;
+    char why[160];
+    if (!sumcheck_verify(cl.data(), n_claims, pr.data(), bn, n_coeffs_per_round, ch.data(), &fin, &recomb, why, sizeof why))
+        return fail(GKRB200_ERR_VERIFY, "%s", why);
+    if (bn) memcpy(challenges_out, ch.data(), (size_t)bn * 32);
+    memcpy(final_claim_out, &fin, 32);
+    if (recomb_out) memcpy(recomb_out, &recomb, 32);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ instrumentation
 extern "C" int gkrb200_stats_reset(gkrb200_ctx* c) {
     if (!c) return fail(GKRB200_ERR_ARG, "null context");

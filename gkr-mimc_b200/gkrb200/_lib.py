@@ -69,6 +69,10 @@ def lib():
     L.gkrb200_interpolate.argtypes = [vp, sz, vp]
     L.gkrb200_to_montgomery.argtypes = [vp, sz, vp]
     L.gkrb200_from_montgomery.argtypes = [vp, sz, vp]
+    L.gkrb200_eval_univariate.argtypes = [vp, sz, vp, vp]
+    L.gkrb200_eval_eq.argtypes = [vp, vp, sz, vp]
+    L.gkrb200_fr_scalar.argtypes = [i32, vp, vp, vp]
+    L.gkrb200_sumcheck_verify.argtypes = [vp, sz, vp, i32, i32, vp, vp, vp]
     L.gkrb200_stats_reset.argtypes = [vp]
     L.gkrb200_stats_get.argtypes = [vp, ctypes.POINTER(Stats)]
     L.gkrb200_set_profiling.argtypes = [vp, i32]

@@ -54,3 +54,21 @@ def Convert(ctx, values, to_montgomery):
     out = fr_empty(v.shape[0])
     check(lib().gkrb200_convert(ctx.handle, _p(v), v.shape[0], _p(out), 1 if to_montgomery else 0))
     return out
+
+
+def EvalUnivariate(coeffs, x):
+    """poly/lagrange.go:31-39 (host; coefficients low -> high)"""
+    c = fr_array(coeffs).reshape(-1, 4)
+    out = fr_empty()
+    check(lib().gkrb200_eval_univariate(_p(c), c.shape[0], _p(fr_array(x)), _p(out)))
+    return out
+
+
+def EvalEq(qPrime, nextQPrime):
+    """poly/eq.go:19-32 (host)"""
+    q, h = fr_array(qPrime).reshape(-1, 4), fr_array(nextQPrime).reshape(-1, 4)
+    if q.shape != h.shape:
+        raise ValueError("EvalEq: the two points have different sizes")
+    out = fr_empty()
+    check(lib().gkrb200_eval_eq(_p(q) if q.shape[0] else None, _p(h) if q.shape[0] else None, q.shape[0], _p(out)))
+    return out

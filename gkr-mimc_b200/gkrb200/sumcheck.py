@@ -36,3 +36,52 @@ def PartialEvals(ctx, eq, X, gate):
     ark = fr_array(gate.ark) if gate.ark is not None else None
     check(lib().gkrb200_round_eval(ctx.handle, _p(e), _p(x0), _p(x1), e.shape[0], gate.kind, _p(ark), _p(out)))
     return out
+
+
+def Verify(claims, proof):
+    """sumcheck.Verify (sumcheck/verifier.go:28-65) -> (challenges, finalClaim, recombChal); raises GkrB200Error
+    (code GKRB200_ERR_VERIFY) where the reference returns an error.  Host-side, like the reference's verifier."""
+    cl = fr_array(claims).reshape(-1, 4)
+    pr = fr_array(proof)
+    bn = pr.shape[0] if pr.ndim == 3 else 0
+    nco = pr.shape[1] if bn else 1
+    chal, fin, rho = fr_empty(bn), fr_empty(), fr_empty()
+    check(lib().gkrb200_sumcheck_verify(_p(cl), cl.shape[0], _p(pr) if bn else None, bn, nco, _p(chal) if bn else None, _p(fin), _p(rho)))
+    return chal, fin, rho
+
+
+def Evaluation(ctx, gate, qPrimes, claims, *X):
+    """sumcheck.Evaluation (sumcheck/instance.go:49-68): sum_x Eq(x) * gate(X(x)) with Eq = sum_j rho^j eq(qPrimes[j], .),
+    rho = GetChallenge(claims) when there are several qPrimes.  The gate values are formed on the device and
+    sum_x eq(q, x) g(x) is MultiLin.Evaluate of g at q, also on the device."""
+    import numpy as np
+    from .common import GetChallenge
+    q = fr_array(qPrimes)
+    n_q, bn = q.shape[0], q.shape[1]
+    x0 = fr_array(X[0]).reshape(-1, 4)
+    if gate.kind == GATE_CIPHER:
+        t = ctx.fr_batch(1, x0, fr_array(X[1]).reshape(-1, 4))
+        t = ctx.fr_batch(1, t, np.ascontiguousarray(np.broadcast_to(gate.ark, t.shape)))
+        g = ctx.fr_batch(3, t)
+    else:
+        g = x0
+    L = lib()
+    res, pw = None, None
+    if claims is None or len(claims) < 1:
+        n_q = 1  # prover.go:117-119: without claims only the first qPrime is used
+    rho = GetChallenge(claims) if n_q > 1 else None
+    for j in range(n_q):
+        e = fr_empty()
+        check(L.gkrb200_mle_evaluate(ctx.handle, _p(g), g.shape[0], _p(np.ascontiguousarray(q[j])) if bn else None, _p(e)))
+        if j == 0:
+            res = e
+            continue
+        pw = rho.copy() if pw is None else _scalar(0, pw, rho)
+        res = _scalar(1, res, _scalar(0, e, pw))
+    return res
+
+
+def _scalar(op, a, b):
+    out = fr_empty()
+    check(lib().gkrb200_fr_scalar(op, _p(fr_array(a)), _p(fr_array(b)), _p(out)))
+    return out

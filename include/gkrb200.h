@@ -141,6 +141,19 @@ int gkrb200_interpolate(const uint64_t *evals, size_t n, uint64_t *coeffs_out);
 int gkrb200_to_montgomery(const uint64_t *in, size_t n, uint64_t *out);
 int gkrb200_from_montgomery(const uint64_t *in, size_t n, uint64_t *out);
 
+/* poly.EvalUnivariate (poly/lagrange.go:31-39): coefficients low -> high, n >= 1                            */
+int gkrb200_eval_univariate(const uint64_t *coeffs, size_t n, const uint64_t *x, uint64_t *out);
+/* poly.EvalEq (poly/eq.go:19-32): prod_i (1 - q_i - h_i + 2 q_i h_i)                                      */
+int gkrb200_eval_eq(const uint64_t *q, const uint64_t *h, size_t n, uint64_t *out);
+/* scalar fr.Element methods for host code above the ABI (gate.Eval in the verifier and in tests):
+ * op 0 = Mul, 1 = Add, 2 = Sub, 3 = x^7 (b ignored), 4 = Inverse (b ignored, 0 -> 0)                     */
+int gkrb200_fr_scalar(int op, const uint64_t *a, const uint64_t *b, uint64_t *out);
+/* sumcheck.Verify(claims, proof) (sumcheck/verifier.go:28-65): proof = bn rounds of n_coeffs_per_round coefficients.
+ * Writes the bn challenges, the final claim P_last(r_last) and (if not NULL) the recombination challenge
+ * GetChallenge(claims).  Returns 0, or GKRB200_ERR_VERIFY when a round fails P(0)+P(1) == expected.       */
+int gkrb200_sumcheck_verify(const uint64_t *claims, size_t n_claims, const uint64_t *proof, int bn, int n_coeffs_per_round,
+                            uint64_t *challenges_out, uint64_t *final_claim_out, uint64_t *recomb_out);
+
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 typedef struct {
     uint64_t launches_total;      /* kernels launched since the last reset                               */

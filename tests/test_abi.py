@@ -107,3 +107,61 @@ def test_argument_errors_before_any_device_work():
     assert L.gkrb200_interpolate(out.ctypes.data_as(ctypes.c_void_p), 13, out.ctypes.data_as(ctypes.c_void_p)) == -1
     h = ctypes.c_void_p()
     assert L.gkrb200_init(ctypes.byref(h), 0, 99, None) == -1
+
+
+def test_host_verifier_pieces_match_oracle(oracle):
+    """poly.EvalUnivariate, poly.EvalEq, scalar fr.Element methods and sumcheck.Verify run on the host inside the product
+    (sumcheck/verifier.go:28-65, poly/lagrange.go:31-39, poly/eq.go:19-32); checked against the oracle without a GPU."""
+    import gkrb200
+    from gkrb200.sumcheck import _scalar
+    rng = np.random.default_rng(11)
+    rnd = lambda n: oracle.to_mont([int.from_bytes(rng.bytes(40), "little") % oracle.Q for _ in range(n)]).reshape(n, 4)
+    for n in (1, 2, 9, 91):
+        c, x = rnd(n), rnd(1)[0]
+        assert np.array_equal(gkrb200.poly.EvalUnivariate(c, x), oracle.eval_univariate(c, x))
+    for n in (0, 1, 5, 22):
+        q, h = rnd(n), rnd(n)
+        assert np.array_equal(gkrb200.poly.EvalEq(q, h), oracle.eval_eq(q, h))
+    Q = oracle.Q
+    edge = oracle.to_mont([0, 1, Q - 1, Q // 2, (1 << 253) - 1, 2]).reshape(-1, 4)
+    for a in list(edge) + list(rnd(4)):
+        for b in list(edge) + list(rnd(2)):
+            assert np.array_equal(_scalar(0, a, b), oracle.fr_mul(a, b))
+            assert np.array_equal(_scalar(1, a, b), oracle.fr_add(a, b))
+            assert np.array_equal(_scalar(2, a, b), oracle.fr_sub(a, b))
+        a7 = oracle.fr_mul(oracle.fr_mul(oracle.fr_mul(a, a), oracle.fr_mul(a, a)), oracle.fr_mul(oracle.fr_mul(a, a), a))
+        assert np.array_equal(_scalar(3, a, a), a7)
+        inv = _scalar(4, a, a)
+        if np.any(a):
+            assert np.array_equal(oracle.fr_mul(inv, a), oracle.to_mont([1]).reshape(4))
+        else:
+            assert not np.any(inv)
+    # sumcheck.Verify on the oracle prover's transcripts: cipher gate (1 claim) and 10-claim identity (sumcheck/testing.go:11-57)
+    for bn in (0, 1, 4, 7):
+        n = 1 << bn
+        L = oracle.to_mont(list(range(n))).reshape(n, 4)
+        q = oracle.random_fr_array(bn).reshape(1, bn, 4)
+        ark = oracle.to_mont([145646]).reshape(4)
+        claim = oracle.evaluation(1, ark, q, None, L, L).reshape(1, 4)
+        proof, chal, fin = oracle.sumcheck_prove([L, L], q, claim, 1, ark)
+        ch2, final, rho = gkrb200.sumcheck.Verify(claim, proof)
+        orc, och, ofin, orho = oracle.sumcheck_verify(claim, proof)
+        assert orc == 0 and np.array_equal(ch2, och) and np.array_equal(final, ofin) and np.array_equal(rho, orho)
+        assert np.array_equal(ch2, chal)
+        if bn:
+            bad = proof.copy()
+            bad[bn - 1, 3, 0] ^= np.uint64(1)
+            with pytest.raises(gkrb200.GkrB200Error) as e:
+                gkrb200.sumcheck.Verify(claim, bad)
+            assert e.value.code == -6 and "round %d" % (bn - 1) in str(e.value)
+        qs = oracle.to_mont([i * j + i for i in range(10) for j in range(bn)]).reshape(10, bn, 4)
+        claims = np.stack([oracle.evaluation(0, None, qs[i:i + 1], None, L) for i in range(10)])
+        proof, chal, fin = oracle.sumcheck_prove([L], qs, claims, 0)
+        ch2, final, rho = gkrb200.sumcheck.Verify(claims, proof)
+        orc, och, ofin, orho = oracle.sumcheck_verify(claims, proof)
+        assert orc == 0 and np.array_equal(ch2, och) and np.array_equal(final, ofin) and np.array_equal(rho, orho)
+    L_ = gkrb200.lib()
+    out = np.zeros(4, dtype=np.uint64)
+    assert L_.gkrb200_eval_univariate(None, 3, out.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == -1
+    assert L_.gkrb200_fr_scalar(9, out.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == -1
+    assert L_.gkrb200_sumcheck_verify(None, 0, None, 0, 9, None, out.ctypes.data_as(ctypes.c_void_p), None) == -1
