@@ -1524,6 +1524,12 @@ extern "C" int gkrb200_from_montgomery(const uint64_t* in, size_t n, uint64_t* o
     return 0;
 }
 
+// hash.Arks[round] (hash/ark.go:13-337), the constant examples.MimcCircuit() gives layer round+3 (examples/mimc.go:29)
+extern "C" int gkrb200_mimc_ark(int round, uint64_t* out) {
+    if (!out || round < 0 || round >= H::MIMC_ROUNDS) return fail(GKRB200_ERR_ARG, "mimc_ark: round %d out of range (0..%d)", round, H::MIMC_ROUNDS - 1);
+    memcpy(out, &H::ARKS[round], 32);
+    return 0;
+}
 // poly.EvalUnivariate (poly/lagrange.go:31-39), poly.EvalEq (poly/eq.go:19-32), scalar fr.Element methods, sumcheck.Verify
 extern "C" int gkrb200_eval_univariate(const uint64_t* coeffs, size_t n, const uint64_t* x, uint64_t* out) {
     if (!coeffs || !x || !out || n < 1) return fail(GKRB200_ERR_ARG, "null argument or empty polynomial");

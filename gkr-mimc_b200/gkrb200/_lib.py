@@ -69,6 +69,7 @@ def lib():
     L.gkrb200_interpolate.argtypes = [vp, sz, vp]
     L.gkrb200_to_montgomery.argtypes = [vp, sz, vp]
     L.gkrb200_from_montgomery.argtypes = [vp, sz, vp]
+    L.gkrb200_mimc_ark.argtypes = [i32, vp]
     L.gkrb200_eval_univariate.argtypes = [vp, sz, vp, vp]
     L.gkrb200_eval_eq.argtypes = [vp, vp, sz, vp]
     L.gkrb200_fr_scalar.argtypes = [i32, vp, vp, vp]

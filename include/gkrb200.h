@@ -141,6 +141,8 @@ int gkrb200_interpolate(const uint64_t *evals, size_t n, uint64_t *coeffs_out);
 int gkrb200_to_montgomery(const uint64_t *in, size_t n, uint64_t *out);
 int gkrb200_from_montgomery(const uint64_t *in, size_t n, uint64_t *out);
 
+/* hash.Arks[round], round 0..90 (hash/ark.go:13-337): the constant of the cipher gate of layer round+3 (examples/mimc.go:29) */
+int gkrb200_mimc_ark(int round, uint64_t *out);
 /* poly.EvalUnivariate (poly/lagrange.go:31-39): coefficients low -> high, n >= 1                            */
 int gkrb200_eval_univariate(const uint64_t *coeffs, size_t n, const uint64_t *x, uint64_t *out);
 /* poly.EvalEq (poly/eq.go:19-32): prod_i (1 - q_i - h_i + 2 q_i h_i)                                      */

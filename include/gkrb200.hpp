@@ -53,7 +53,28 @@ inline Element ToRegular(const Element& x) {
     check(gkrb200_from_montgomery(x.data(), 1, out.data()));
     return out;
 }
+// scalar fr.Element methods (host): Mul, Add, Sub, the S-box x^7, Inverse
+inline Element scalar(int op, const Element& a, const Element& b) {
+    Element out;
+    check(gkrb200_fr_scalar(op, a.data(), b.data(), out.data()));
+    return out;
+}
+inline Element Mul(const Element& a, const Element& b) { return scalar(0, a, b); }
+inline Element Add(const Element& a, const Element& b) { return scalar(1, a, b); }
+inline Element Sub(const Element& a, const Element& b) { return scalar(2, a, b); }
+inline Element Exp7(const Element& a) { return scalar(3, a, a); }
+inline Element Inverse(const Element& a) { return scalar(4, a, a); }
+inline Element One() { return SetUint64(1); }
 }  // namespace fr
+
+namespace detail {
+// pointer to the elements of a (possibly empty) vector: an empty Go slice still has a valid base pointer, so the ABI never sees NULL for one
+template <class V>
+inline auto ptr(V& v) -> decltype(v[0].data()) {
+    static fr::Element scratch{};
+    return v.empty() ? const_cast<decltype(v[0].data())>(scratch.data()) : v[0].data();
+}
+}  // namespace detail
 
 // One device context = the reference's package-global pool + worker goroutines (poly/pool.go, sumcheck/worker.go).
 class Device {
@@ -79,7 +100,7 @@ inline std::vector<fr::Element> RandomFrArray(size_t n) {
 // common.GetChallenge(seed) == hash.MimcHash(seed)
 inline fr::Element GetChallenge(const std::vector<fr::Element>& seed) {
     fr::Element out;
-    check(gkrb200_mimc_hash(seed.empty() ? nullptr : seed[0].data(), seed.size(), out.data()));
+    check(gkrb200_mimc_hash(detail::ptr(seed), seed.size(), out.data()));
     return out;
 }
 }  // namespace common
@@ -93,22 +114,35 @@ using MultiLin = std::vector<fr::Element>;
 // MultiLin.Fold(r): the table keeps its first half (poly/multilin.go:19-23)
 inline void Fold(Device& d, MultiLin& m, const fr::Element& r) {
     MultiLin out(m.size() / 2);
-    check(gkrb200_fold(d.handle(), m[0].data(), m.size(), r.data(), out.empty() ? nullptr : out[0].data()));
+    check(gkrb200_fold(d.handle(), m[0].data(), m.size(), r.data(), detail::ptr(out)));
     m.swap(out);
 }
 inline fr::Element Evaluate(Device& d, const MultiLin& m, const std::vector<fr::Element>& coordinates) {
     fr::Element out;
-    check(gkrb200_mle_evaluate(d.handle(), m[0].data(), m.size(), coordinates.empty() ? nullptr : coordinates[0].data(), out.data()));
+    check(gkrb200_mle_evaluate(d.handle(), m[0].data(), m.size(), detail::ptr(coordinates), out.data()));
     return out;
 }
 inline MultiLin FoldedEqTable(Device& d, const std::vector<fr::Element>& qPrime) {
     MultiLin out((size_t)1 << qPrime.size());
-    check(gkrb200_eq_table(d.handle(), qPrime.empty() ? nullptr : qPrime[0].data(), 1, (int)qPrime.size(), nullptr, out[0].data()));
+    check(gkrb200_eq_table(d.handle(), detail::ptr(qPrime), 1, (int)qPrime.size(), nullptr, out[0].data()));
     return out;
 }
 inline std::vector<fr::Element> InterpolateOnRange(const std::vector<fr::Element>& values) {
     std::vector<fr::Element> out(values.size());
-    check(gkrb200_interpolate(values[0].data(), values.size(), out[0].data()));
+    check(gkrb200_interpolate(detail::ptr(values), values.size(), detail::ptr(out)));
+    return out;
+}
+// poly.EvalUnivariate (poly/lagrange.go:31-39), coefficients low -> high
+inline fr::Element EvalUnivariate(const std::vector<fr::Element>& coeffs, const fr::Element& x) {
+    fr::Element out;
+    check(gkrb200_eval_univariate(detail::ptr(coeffs), coeffs.size(), x.data(), out.data()));
+    return out;
+}
+// poly.EvalEq (poly/eq.go:19-32)
+inline fr::Element EvalEq(const std::vector<fr::Element>& qPrime, const std::vector<fr::Element>& nextQPrime) {
+    if (qPrime.size() != nextQPrime.size()) throw Panic(GKRB200_ERR_ARG, "EvalEq: the two points have different sizes");
+    fr::Element out;
+    check(gkrb200_eval_eq(detail::ptr(qPrime), detail::ptr(nextQPrime), qPrime.size(), out.data()));
     return out;
 }
 }  // namespace poly
@@ -121,12 +155,19 @@ struct Gate {
     std::string ID() const { return kind == GKRB200_GATE_CIPHER ? "cipher" : (kind == GKRB200_GATE_IDENTITY ? "identity" : ""); }
     int Degree() const { return kind == GKRB200_GATE_CIPHER ? 7 : 1; }  // cipher.go:68-70, copy.go:30-32
     bool nil() const { return kind < 0; }
+    // Gate.Eval (cipher.go:45-55: (vL + vR + Ark)^7; copy.go:20-22: vL)
+    fr::Element Eval(const std::vector<fr::Element>& xs) const {
+        if (kind == GKRB200_GATE_IDENTITY) return xs.at(0);
+        if (kind != GKRB200_GATE_CIPHER) throw Panic(GKRB200_ERR_ARG, "Eval on a nil gate");
+        return fr::Exp7(fr::Add(fr::Add(xs.at(1), ark), xs.at(0)));
+    }
 };
 struct Layer {
     Gate gate;
     std::vector<int> In, Out;
 };
 struct Circuit : std::vector<Layer> {
+    using std::vector<Layer>::vector;  // make(circuit.Circuit, n)
     // circuit.go:70-79 (an input layer has no inputs and no gate; anything else inconsistent panics)
     bool IsInputLayer(int layer) const {
         const Layer& l = (*this)[(size_t)layer];
@@ -157,6 +198,19 @@ public:
         check(gkrb200_assign_layer_to_host(d_->handle(), layer, out[0].data(), n_));
         return out;
     }
+    // a[layer].Evaluate(coordinates) without copying the table off the device
+    fr::Element Evaluate(int layer, const std::vector<fr::Element>& coordinates) const {
+        fr::Element out;
+        check(gkrb200_assign_layer_evaluate(d_->handle(), layer, detail::ptr(coordinates), bn_, out.data()));
+        return out;
+    }
+    // Assignment.InputsOfLayer (circuit/assignment.go:46-57): host copies of the input tables of a layer
+    template <class CircuitT>
+    std::vector<poly::MultiLin> InputsOfLayer(const CircuitT& c, int layer) const {
+        std::vector<poly::MultiLin> xs;
+        for (int in : c[(size_t)layer].In) xs.push_back((*this)[in]);
+        return xs;
+    }
     size_t size() const { return GKRB200_MIMC_LAYERS; }
     int bn() const { return bn_; }
     Device& device() const { return *d_; }
@@ -174,8 +228,13 @@ inline circuit::Gate NewCipherGate(const fr::Element& ark) { return circuit::Gat
 }  // namespace gates
 
 namespace examples {
-// examples/mimc.go:10-37.  hash.Arks are not exported by the C ABI: the cipher gates of this description carry only their
-// position (the device holds the constants); Assign/Prove accept exactly this circuit shape.
+// hash.Arks[i] (hash/ark.go:13-337)
+inline fr::Element Ark(int i) {
+    fr::Element a;
+    check(gkrb200_mimc_ark(i, a.data()));
+    return a;
+}
+// examples/mimc.go:10-37.  Assign/Prove accept exactly this circuit (same wiring, same gates, same constants).
 inline circuit::Circuit MimcCircuit() {
     circuit::Circuit c;
     c.resize(GKRB200_MIMC_LAYERS);
@@ -183,7 +242,7 @@ inline circuit::Circuit MimcCircuit() {
     c[2].gate = gates::IdentityGate();
     for (int i = 0; i < 91; i++) {
         c[(size_t)i + 3].In = {2, i == 0 ? 1 : i + 2};
-        c[(size_t)i + 3].gate.kind = GKRB200_GATE_CIPHER;
+        c[(size_t)i + 3].gate = gates::NewCipherGate(Ark(i));
     }
     return circuit::BuildCircuit(c);
 }
@@ -191,7 +250,7 @@ inline bool IsMimcCircuit(const circuit::Circuit& c) {
     if (c.size() != GKRB200_MIMC_LAYERS) return false;
     const circuit::Circuit m = MimcCircuit();
     for (size_t l = 0; l < c.size(); l++)
-        if (c[l].In != m[l].In || c[l].gate.kind != m[l].gate.kind) return false;
+        if (c[l].In != m[l].In || c[l].gate.kind != m[l].gate.kind || (c[l].gate.kind == GKRB200_GATE_CIPHER && c[l].gate.ark != m[l].gate.ark)) return false;
     return true;
 }
 }  // namespace examples
@@ -222,12 +281,52 @@ inline std::tuple<Proof, std::vector<fr::Element>, std::vector<fr::Element>> Pro
         q.insert(q.end(), qp.begin(), qp.end());
     }
     if (X.at(0).size() != ((size_t)1 << bn)) throw Panic(GKRB200_ERR_ARG, "inconsistent sizes : the table and qPrime disagree");  // prover.go:54
-    check(gkrb200_sumcheck_prove(d.handle(), X[0][0].data(), X.size() > 1 ? X[1][0].data() : nullptr, bn, q.empty() ? nullptr : q[0].data(), qPrimes.size(),
-                                 claims.empty() ? nullptr : claims[0].data(), claims.size(), gate.kind, gate.kind == GKRB200_GATE_CIPHER ? gate.ark.data() : nullptr,
-                                 flat.empty() ? nullptr : flat[0].data(), challenges.empty() ? nullptr : challenges[0].data(), fin[0].data()));
+    check(gkrb200_sumcheck_prove(d.handle(), X[0][0].data(), X.size() > 1 ? X[1][0].data() : nullptr, bn, detail::ptr(q), qPrimes.size(),
+                                 detail::ptr(claims), claims.size(), gate.kind, gate.kind == GKRB200_GATE_CIPHER ? gate.ark.data() : nullptr,
+                                 detail::ptr(flat), detail::ptr(challenges), fin[0].data()));
     Proof proof((size_t)bn);
     for (int k = 0; k < bn; k++) proof[(size_t)k].assign(flat.begin() + (size_t)k * nco, flat.begin() + (size_t)(k + 1) * nco);
     return {proof, challenges, fin};
+}
+// sumcheck.Verify(claims, proof) -> (challenges, finalClaim, recombChal, err)   sumcheck/verifier.go:28-65
+inline std::tuple<std::vector<fr::Element>, fr::Element, fr::Element, std::string> Verify(const std::vector<fr::Element>& claims, const Proof& proof) {
+    const int bn = (int)proof.size();
+    const size_t nco = bn ? proof[0].size() : 1;
+    std::vector<fr::Element> flat, challenges((size_t)bn);
+    for (const auto& round : proof) {
+        if (round.size() != nco) throw Panic(GKRB200_ERR_ARG, "ragged sumcheck proof");
+        flat.insert(flat.end(), round.begin(), round.end());
+    }
+    fr::Element fin{}, recomb{};
+    const int rc = gkrb200_sumcheck_verify(detail::ptr(claims), claims.size(), detail::ptr(flat), bn, (int)nco,
+                                           detail::ptr(challenges), fin.data(), recomb.data());
+    if (rc == GKRB200_ERR_VERIFY) return {{}, {}, {}, gkrb200_last_error()};
+    check(rc);
+    return {challenges, fin, recomb, ""};
+}
+// sumcheck.Evaluation(gate, qPrime, claims, X...)   sumcheck/instance.go:49-68.  sum_x Eq(x) gate(X(x)), Eq = sum_j rho^j eq(q_j, .):
+// the gate values are formed on the device and sum_x eq(q, x) g(x) is MultiLin.Evaluate(g, q), also on the device.
+inline fr::Element Evaluation(Device& d, const circuit::Gate& gate, const std::vector<std::vector<fr::Element>>& qPrimes, const std::vector<fr::Element>& claims,
+                              const std::vector<poly::MultiLin>& X) {
+    const size_t n = X.at(0).size();
+    poly::MultiLin g = X[0];
+    if (gate.kind == GKRB200_GATE_CIPHER) {
+        poly::MultiLin arks(n, gate.ark), t(n);
+        check(gkrb200_fr_batch(d.handle(), 1, X[0][0].data(), X.at(1)[0].data(), n, t[0].data()));
+        check(gkrb200_fr_batch(d.handle(), 1, t[0].data(), arks[0].data(), n, t[0].data()));
+        check(gkrb200_fr_batch(d.handle(), 3, t[0].data(), nullptr, n, g[0].data()));
+    }
+    const size_t n_q = claims.empty() ? 1 : qPrimes.size();  // prover.go:117-119: without claims only qPrimes[0] is used
+    fr::Element res = poly::Evaluate(d, g, qPrimes.at(0));
+    if (n_q > 1) {
+        const fr::Element rho = common::GetChallenge(claims);
+        fr::Element pw = rho;
+        for (size_t j = 1; j < n_q; j++) {
+            res = fr::Add(res, fr::Mul(poly::Evaluate(d, g, qPrimes[j]), pw));
+            pw = fr::Mul(pw, rho);
+        }
+    }
+    return res;
 }
 }  // namespace sumcheck
 
@@ -275,14 +374,14 @@ inline Proof ProofFromVec(const circuit::Circuit& c, int bn, const std::vector<f
 // gkr.Prove(c, a, qPrime)
 inline Proof Prove(const circuit::Circuit& c, const circuit::Assignment& a, const std::vector<fr::Element>& qPrime) {
     std::vector<fr::Element> v(gkrb200_proof_vec_len(a.bn()));
-    check(gkrb200_gkr_prove_mimc(a.device().handle(), qPrime.empty() ? nullptr : qPrime[0].data(), (int)qPrime.size(), v[0].data(), GKRB200_PROOF_MONTGOMERY));
+    check(gkrb200_gkr_prove_mimc(a.device().handle(), detail::ptr(qPrime), (int)qPrime.size(), v[0].data(), GKRB200_PROOF_MONTGOMERY));
     return ProofFromVec(c, a.bn(), v);
 }
 // gkr.Verify(c, proof, inputs, outputs, qPrime): inputs/outputs are the layers 0, 1 and 93 of the assignment held by the device.
 // Returns "" when the proof is accepted, else the reason (Go: error).
 inline std::string Verify(const circuit::Circuit&, const Proof& proof, const circuit::Assignment& a, const std::vector<fr::Element>& qPrime) {
     const std::vector<fr::Element> v = GkrProofToVec(proof);
-    const int rc = gkrb200_gkr_verify_mimc(a.device().handle(), v[0].data(), a.bn(), qPrime.empty() ? nullptr : qPrime[0].data(), GKRB200_PROOF_MONTGOMERY);
+    const int rc = gkrb200_gkr_verify_mimc(a.device().handle(), v[0].data(), a.bn(), detail::ptr(qPrime), GKRB200_PROOF_MONTGOMERY);
     if (rc == 0) return "";
     if (rc == GKRB200_ERR_VERIFY) return gkrb200_last_error();
     throw Panic(rc, gkrb200_last_error());

@@ -195,6 +195,46 @@ def test_sumcheck_multi_identity(ctx, oracle, bn, ninst):
     _check_sumcheck(ctx, oracle, [L], claims, qs, gkrb200.gates.IdentityGate(), oracle.GATE_IDENTITY, None)
 
 
+@pytest.mark.parametrize("bn", [0, 1, 5, 12])
+def test_sumcheck_evaluation_and_host_verifier(ctx, oracle, bn):
+    """sumcheck.Evaluation (sumcheck/instance.go:49-68) formed on the device (gate values + MLE evaluation) and sumcheck.Verify
+    (sumcheck/verifier.go:28-65) on the device prover's transcript: genericTest of sumcheck/prover_test.go:43-81"""
+    import gkrb200
+    n = 1 << bn
+    L = gkrb200.common.SetUint64(range(n))
+    R = rand_fr(np.random.default_rng(77 + bn), n)
+    ark = gkrb200.common.SetUint64([145646])[0]
+    q = oracle.random_fr_array(bn).reshape(1, bn, 4)
+    gate = gkrb200.gates.CipherGate(ark)
+    claim = gkrb200.sumcheck.Evaluation(ctx, gate, q, None, L, R)
+    assert np.array_equal(claim, oracle.evaluation(oracle.GATE_CIPHER, ark, q, None, L, R))
+    proof, chal, fin = gkrb200.sumcheck.Prove(ctx, [L, R], q, claim.reshape(1, 4), gate)
+    vchal, final, rho = gkrb200.sumcheck.Verify(claim.reshape(1, 4), proof)
+    orc, ochal, ofinal, orho = oracle.sumcheck_verify(claim.reshape(1, 4), proof)
+    assert orc == 0 and np.array_equal(vchal, ochal) and np.array_equal(final, ofinal) and np.array_equal(rho, orho)
+    assert np.array_equal(vchal, chal)
+    t = oracle.fr_add(oracle.fr_add(fin[1], fin[2]), ark)
+    t2 = oracle.fr_mul(t, t)
+    t7 = oracle.fr_mul(oracle.fr_mul(oracle.fr_mul(t2, t), oracle.fr_mul(t2, t)), t)
+    assert np.array_equal(final, oracle.fr_mul(t7, fin[0]))
+    ninst = 10
+    qs = np.stack([gkrb200.common.SetUint64([i * j + i for j in range(bn)]).reshape(bn, 4) for i in range(ninst)])
+    idg = gkrb200.gates.IdentityGate()
+    claims = np.stack([gkrb200.sumcheck.Evaluation(ctx, idg, qs[i:i + 1], None, L) for i in range(ninst)])
+    assert np.array_equal(claims, np.stack([oracle.evaluation(oracle.GATE_IDENTITY, None, qs[i:i + 1], None, L) for i in range(ninst)]))
+    assert np.array_equal(gkrb200.sumcheck.Evaluation(ctx, idg, qs, claims, L), oracle.evaluation(oracle.GATE_IDENTITY, None, qs, claims, L))
+    proof, chal, fin = gkrb200.sumcheck.Prove(ctx, [L], qs, claims, idg)
+    vchal, final, rho = gkrb200.sumcheck.Verify(claims, proof)
+    assert np.array_equal(vchal, chal) and np.array_equal(final, oracle.fr_mul(fin[0], fin[1]))
+    assert np.array_equal(rho, gkrb200.common.GetChallenge(claims))
+    if bn:
+        bad = proof.copy()
+        bad[0, 1, 2] ^= np.uint64(8)
+        with pytest.raises(gkrb200.GkrB200Error) as e:
+            gkrb200.sumcheck.Verify(claims, bad)
+        assert e.value.code == -6
+
+
 def test_sumcheck_golden_digests(ctx, oracle):
     """tests/golden/sumcheck_cipher.json: claim, sha256 of the round coefficients, first challenge (bn 1..4)"""
     import gkrb200
