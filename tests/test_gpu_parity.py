@@ -379,6 +379,36 @@ def test_gkr_full_size_properties(oracle, bn):
         big.close()
 
 
+def test_sumcheck_standalone_2pow20(oracle):
+    """BASELINE config 2: standalone sumcheck of eq * gate over 2^20-entry tables on one B200 (sumcheck/prover_test.go style):
+    InitializeCipherGateInstance(20) exactly (L = R = ramp, ark 145646) and a random-table variant, every round polynomial,
+    challenge and final claim compared with the oracle, plus the 91-claim identity sumcheck (BenchmarkMultiIdentity) at 2^20."""
+    import gkrb200
+    bn = 20
+    n = 1 << bn
+    big = gkrb200.Context(device=0, max_bn=bn)
+    oracle.set_threads(os.cpu_count() or 1)
+    try:
+        ark = gkrb200.common.SetUint64([145646])[0]
+        gate = gkrb200.gates.CipherGate(ark)
+        q = oracle.random_fr_array(bn).reshape(1, bn, 4)
+        ramp = gkrb200.common.SetUint64(range(n))
+        for L, R in ((ramp, ramp.copy()), (fast_fr(41, n), fast_fr(42, n))):
+            claim = gkrb200.sumcheck.Evaluation(big, gate, q, None, L, R).reshape(1, 4)
+            assert np.array_equal(claim[0], oracle.evaluation(oracle.GATE_CIPHER, ark, q, None, L, R))
+            _check_sumcheck(big, oracle, [L, R], claim, q, gate, oracle.GATE_CIPHER, ark)
+        ninst = 91
+        qs = fast_fr(43, ninst * bn).reshape(ninst, bn, 4)
+        idg = gkrb200.gates.IdentityGate()
+        L = fast_fr(44, n)
+        claims = np.stack([gkrb200.poly.Evaluate(big, L, qs[i]) for i in range(ninst)])
+        assert np.array_equal(claims[17], oracle.evaluate(L, qs[17]))
+        _check_sumcheck(big, oracle, [L], claims, qs, idg, oracle.GATE_IDENTITY, None)
+    finally:
+        oracle.set_threads(min(8, os.cpu_count() or 1))
+        big.close()
+
+
 # ----------------------------------------------------------------------------- factored cipher round (k_round_cf)
 @pytest.mark.parametrize("bn", [1, 2, 3, 5, 8, 11, 14, 16])
 @pytest.mark.parametrize("par8_max", [0, 16, 1 << 20])
