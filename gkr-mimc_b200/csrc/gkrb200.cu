@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/gkrb200.h"
@@ -62,18 +63,22 @@ struct Nccl {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    bool load() {
-        if (h) return true;
-        // torch's bundled libnccl.so.2 is reused when it is already mapped in the process (same SONAME)
-        h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (!h) return false;
-        GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
-        CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
-        CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
-        AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
-        GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-        return GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+    std::once_flag once;
+    bool ok = false;
+    bool load() {  // several pipelines (host threads) of one process initialise their communicators concurrently
+        std::call_once(once, [this] {
+            // torch's bundled libnccl.so.2 is reused when it is already mapped in the process (same SONAME)
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) return;
+            GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+            CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+            AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+            GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+            ok = GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+        });
+        return ok;
     }
 };
 static Nccl g_nccl;
@@ -368,6 +373,7 @@ static H::Fr wide_to_fr(const volatile uint64_t* w, int wl, int n_ranks, size_t 
 }
 
 // ------------------------------------------------------------------------------------------------ init / free
+static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream);
 extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* stream) {
     if (!out || max_bn < 0 || max_bn > 26) return fail(GKRB200_ERR_ARG, "bad arguments to gkrb200_init (max_bn=%d)", max_bn);
     int ndev = 0;
@@ -377,13 +383,21 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     if (device < 0 || device >= ndev) return fail(GKRB200_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
     gkrb200_ctx* c = new gkrb200_ctx();
+    const int rc = init_ctx(c, device, max_bn, stream);
+    if (rc) {
+        gkrb200_free(c);  // releases whatever was built before the failure
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
     c->device = device;
     c->max_bn = max_bn;
     c->cap = (size_t)1 << max_bn;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
-        delete c;
         return fail(GKRB200_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
     }
     c->n_sm = prop.multiProcessorCount;
@@ -401,7 +415,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
                    (size_t)c->max_grid * MAX_EV + 64 + 8 * 64 + 3 * 32 + 64 + ((size_t)c->n_sm * 8 * 8 * 17 * 4 + 31) / 32;
     cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
     if (me != cudaSuccess) {
-        delete c;
+        c->arena = nullptr;
         return fail(GKRB200_ERR_OOM, "cudaMalloc of %.2f GiB arena failed: %s", total * 32.0 / (1 << 30), cudaGetErrorString(me));
     }
     FrRaw* p = c->arena;
@@ -437,7 +451,6 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cf_kernel(true, n, false), CF_BLOCK1, cf_smem(n, false)));
         c->cf_blocks_per_sm1[n - 7] = nb > 0 ? nb : 1;
     }
-    *out = c;
     return 0;
 }
 
@@ -463,7 +476,7 @@ extern "C" void gkrb200_free(gkrb200_ctx* c) {
 }
 
 extern "C" int gkrb200_comm_unique_id(uint8_t id_out[128]) {
-    if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl: %s", dlerror());
+    if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl.so.2 (or a symbol is missing)");
     ncclUniqueId id;
     NCCL_TRY(g_nccl.GetUniqueId(&id));
     memcpy(id_out, id.internal, 128);
@@ -477,7 +490,7 @@ extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint
     c->log_world = 0;
     while ((1 << c->log_world) < world) c->log_world++;
     if (world == 1) return 0;
-    if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl: %s", dlerror());
+    if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl.so.2 (or a symbol is missing)");
     CUDA_TRY(cudaSetDevice(c->device));
     ncclUniqueId id;
     memcpy(id.internal, uid, 128);
