@@ -165,3 +165,25 @@ def test_host_verifier_pieces_match_oracle(oracle):
     assert L_.gkrb200_eval_univariate(None, 3, out.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == -1
     assert L_.gkrb200_fr_scalar(9, out.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == -1
     assert L_.gkrb200_sumcheck_verify(None, 0, None, 0, 9, None, out.ctypes.data_as(ctypes.c_void_p), None) == -1
+
+
+def test_header_is_plain_c(tmp_path):
+    """cgo compiles include/gkrb200.h as C: it must be valid C99 on its own (no C++, torch or CUDA types) and link against the library"""
+    import gkrb200
+    src = tmp_path / "use.c"
+    src.write_text('#include "gkrb200.h"\n#include <stdio.h>\n'
+                   'int main(void) {\n'
+                   '    uint64_t twelve[4] = {12, 0, 0, 0}, m[4], h[4], r[4];\n'
+                   '    if (gkrb200_to_montgomery(twelve, 1, m) || gkrb200_mimc_hash(m, 1, h) || gkrb200_from_montgomery(h, 1, r)) return 1;\n'
+                   '    printf("%016llx%016llx%016llx%016llx %zu %s\\n", (unsigned long long)r[3], (unsigned long long)r[2], (unsigned long long)r[1],\n'
+                   '           (unsigned long long)r[0], gkrb200_proof_vec_len(22), gkrb200_version());\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "use"
+    lib_dir = os.path.dirname(gkrb200._lib.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L" + lib_dir, "-lgkrb200", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    hexval, veclen, _ = out.stdout.split(" ", 2)
+    assert int(hexval, 16) == 1808205620575546259657963589762746470347087906694759866517376279978241663265  # hash/hash_test.go:21-27 through C
+    assert int(veclen) == 1006 * 22 + 183
