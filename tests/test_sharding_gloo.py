@@ -1,4 +1,4 @@
-"""world_size-2 CPU test (gloo) of the multi-GPU decomposition the library implements with NCCL (SURVEY.md
+"""world_size 2/4/8 CPU tests (gloo) of the multi-GPU decomposition the library implements with NCCL (SURVEY.md
 section 5/8e, gkrb200.cu Ctx::sumcheck): rank g owns table entries {i : i mod G == g}; its eq shard is
 s_g * eq(q[0:bn-log2 G], .); per round the ranks exchange only their partial round evaluations; after
 bn-log2 G rounds the G residual entries are gathered and the last rounds are finished identically everywhere.
@@ -80,9 +80,9 @@ def _worker(rank, world, port, bn, kind, q, out):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,bn", [("cipher", 5), ("identity", 4), ("cipher", 1)])
-def test_two_rank_sharded_sumcheck_equals_single(kind, bn):
-    world = 2
+@pytest.mark.parametrize("kind,bn,world", [("cipher", 5, 2), ("identity", 4, 2), ("cipher", 1, 2), ("cipher", 5, 4), ("identity", 4, 8), ("cipher", 3, 8)])
+def test_sharded_sumcheck_equals_single(kind, bn, world):
+    """2, 4 and 8 ranks (the box sizes bench.py runs), incl. bn == log2(world): every rank holds ONE entry per table"""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyref as P
     q = P.random_fr_array(bn + 2)[2:]
@@ -90,4 +90,4 @@ def test_two_rank_sharded_sumcheck_equals_single(kind, bn):
     out = mgr.dict()
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, bn, kind, q, out), nprocs=world, join=True)
-    assert dict(out) == {0: 1, 1: 1}
+    assert dict(out) == {g: 1 for g in range(world)}
