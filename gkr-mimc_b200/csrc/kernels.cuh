@@ -646,16 +646,37 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
 
     if (PAR == 1) {
         for (size_t x = (size_t)blockIdx.x * BLOCK + tid; x < half; x += (size_t)gridDim.x * BLOCK) {
+            // the eq factors are requested first as well (small L1/L2-resident tables, but behind the fold's stores they too waited)
+            const Fr ub = fr_load(a.tA ? a.tB + (x & cmask) : a.tB + x);
+            Fr ua;
+            if (a.tA) ua = fr_load(a.tA + (x >> a.c));
             Fr av, bv;
-            {
-                const Fr b0 = load_fold_one<FOLD>(a.src[0], a.dst[0], x, m2, r);
-                const Fr t0 = load_fold_one<FOLD>(a.src[0], a.dst[0], x + half, m2, r);
-                const Fr b1 = load_fold_one<FOLD>(a.src[1], a.dst[1], x, m2, r);
-                const Fr t1 = load_fold_one<FOLD>(a.src[1], a.dst[1], x + half, m2, r);
+            if (FOLD) {
+                // All eight source entries are requested BEFORE the first fold: the loads and stores are volatile asm, so a
+                // load placed after a store stays after it, and the fold-store-load sequence exposed one DRAM latency per
+                // folded entry (4 long-scoreboard stall sites per pair in profiles/r1_ncu_k_round_cf_fold_opcode_mix.txt).
+                // In place is still safe: a thread reads x, x+half, x+2half, x+3half of each table and writes x, x+half.
+                const Fr l0 = fr_load_stream(a.src[0] + x), h0 = fr_load_stream(a.src[0] + x + m2);
+                const Fr l1 = fr_load_stream(a.src[0] + x + half), h1 = fr_load_stream(a.src[0] + x + half + m2);
+                const Fr l2 = fr_load_stream(a.src[1] + x), h2 = fr_load_stream(a.src[1] + x + m2);
+                const Fr l3 = fr_load_stream(a.src[1] + x + half), h3 = fr_load_stream(a.src[1] + x + half + m2);
+                const Fr b0 = fr_add(l0, fr_mulc(r, fr_sub(h0, l0)));
+                fr_store(a.dst[0] + x, b0);
+                const Fr t0 = fr_add(l1, fr_mulc(r, fr_sub(h1, l1)));
+                fr_store(a.dst[0] + x + half, t0);
+                const Fr b1 = fr_add(l2, fr_mulc(r, fr_sub(h2, l2)));
+                fr_store(a.dst[1] + x, b1);
+                const Fr t1 = fr_add(l3, fr_mulc(r, fr_sub(h3, l3)));
+                fr_store(a.dst[1] + x + half, t1);
                 av = fr_add(fr_add(b0, b1), ark);                 // cipher.go:34-35 on the bottom half
                 bv = fr_add(fr_sub(t0, b0), fr_sub(t1, b1));      // (top + ark) - (bottom + ark)
+            } else {
+                const Fr b0 = fr_load_stream(a.src[0] + x), t0 = fr_load_stream(a.src[0] + x + half);
+                const Fr b1 = fr_load_stream(a.src[1] + x), t1 = fr_load_stream(a.src[1] + x + half);
+                av = fr_add(fr_add(b0, b1), ark);
+                bv = fr_add(fr_sub(t0, b0), fr_sub(t1, b1));
             }
-            Fr u = a.tA ? fr_mulc(fr_load(a.tA + (x >> a.c)), fr_load(a.tB + (x & cmask))) : fr_load(a.tB + x);
+            Fr u = a.tA ? fr_mulc(ua, ub) : ub;
             // m_i = T a^(7-i) b^i as (T * degree-4 monomial) * (degree-3 monomial): the four cubic monomials (6 products),
             // T a, T a^4 and T a b^3 (3 products) give all of m_0..m_6 as products that only feed the sums, and those are
             // accumulated UNREDUCED (fr_mul_acc_wide).  9 Montgomery products per pair instead of 11 for powers + chain.
