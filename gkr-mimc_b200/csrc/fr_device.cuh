@@ -204,6 +204,19 @@ __device__ __forceinline__ void chain4_cin(uint32_t& c0, uint32_t& c1, uint32_t&
     (void)dead;
 }
 
+// m = x * (-q^-1) mod 2^32.  -q^-1 = 0xefffffff = -(2^28 + 1), so m = -(x + (x << 28)): a shift-add and a negation on the
+// ALU pipe instead of one more IMAD on the pipe the wide multiply-adds are bound by (8 per product).
+#ifndef GKR_M_BY_SHIFT
+#define GKR_M_BY_SHIFT 1
+#endif
+__device__ __forceinline__ uint32_t fr_mont_m(uint32_t x) {
+#if GKR_M_BY_SHIFT
+    return 0u - (x + (x << 28));
+#else
+    return x * FR_QINV32;
+#endif
+}
+
 // Montgomery product a*b*2^-256 mod q, inputs canonical (< q), output canonical.
 //
 // P[p] is the accumulator limb at ABSOLUTE position p (weight 2^(32p)) of the accumulator whose
@@ -224,7 +237,7 @@ __device__ __forceinline__ Fr fr_mul_school(const Fr& a, const Fr& b) {
         // columns (i,i+1)..(i+6,i+7) += a_even * b_i
         chain4(S[i], S[i + 1], S[i + 2], S[i + 3], S[i + 4], S[i + 5], S[i + 6], S[i + 7], S[i + 8], a.v[0], a.v[2], a.v[4], a.v[6], bi);
         // m makes limb i of (S + T) vanish
-        const uint32_t m = (S[i] + T[i]) * FR_QINV32;
+        const uint32_t m = fr_mont_m(S[i] + T[i]);
         chain4(S[i], S[i + 1], S[i + 2], S[i + 3], S[i + 4], S[i + 5], S[i + 6], S[i + 7], S[i + 8], q[0], q[2], q[4], q[6], m);
         // columns (i+1,i+2)..(i+7,i+8) += a_odd * b_i, carry-in = carry of the dead limb i
         chain4_cin(T[i + 1], T[i + 2], T[i + 3], T[i + 4], T[i + 5], T[i + 6], T[i + 7], T[i + 8], T[i + 9], a.v[1], a.v[3], a.v[5], a.v[7],
@@ -246,56 +259,53 @@ __device__ __forceinline__ Fr fr_mul_school(const Fr& a, const Fr& b) {
           "r"(Qd[8]), "r"(Qd[9]), "r"(Qd[10]), "r"(Qd[11]), "r"(Qd[12]), "r"(Qd[13]), "r"(Qd[14]), "r"(Qd[15]));
     return fr_reduce_once(t);
 }
-}  // namespace gkr
-#include "fr_kara.cuh"  // hd_mul_k / hd_mul_wide_k: the Karatsuba form (120 instead of 136 wide multiply-adds)
-namespace gkr {
-// The multiplier every kernel uses: GKR_MUL_KARA = 0 (default) the operand-scanning form above, 1 the Karatsuba form of
-// fr_kara.cuh; GKR_ACC_KARA likewise for the plain 512-bit products of fr_mul_acc_wide.  All forms give the same canonical
-// residues (the parity suite passes with each build).  Measured on B200 (profiles/r1_exp_karatsuba.txt): Karatsuba saves 16 of
-// 136 wide multiply-adds per product but its ~100 extra carry-chain adds -- a third of which ptxas issues as IMAD.X /
-// IMAD.MOV on the same fmaheavy pipe -- make it SLOWER: 60.0 vs 66.4 G Fr-mul/s in isolation, 164 vs 151 ms per 2^22 proof.
-#ifndef GKR_MUL_KARA
-#define GKR_MUL_KARA 0
-#endif
-#ifndef GKR_ACC_KARA
-#define GKR_ACC_KARA 0
-#endif
-__device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
-#if GKR_MUL_KARA
-    return hd_mul_k(a, b);
-#else
-    return fr_mul_school(a, b);
-#endif
-}
+__device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) { return fr_mul_school(a, b); }
 __device__ __forceinline__ Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
 
-// Out-of-line copy of the multiplier (register ABI, no stack: 16 words in, 8 out).  Kernels that issue many
-// multiplications per work item call this one ~3 KB body instead of inlining it 20-50 times: the round kernels
-// shrink from ~50 KB to a few KB of SASS, which keeps them inside the instruction cache (profiles/: the inlined
-// v1/v2 kernels showed no_instruction stalls and a 40 us floor for one-wave launches).
+// Out-of-line copy of the multiplier (register ABI, no stack: 16 words in, 8 out) for the small, latency-bound kernels:
+// one ~3 KB body instead of 20-50 inlined copies keeps their cold instruction fetch short (profiles/: the fully inlined
+// round kernels of round 1 had a 40 us floor for one-wave launches).  The big-round kernels inline the multiplier
+// (GKR_INLINE_BIG, kernels.cuh): the call ABI costs ~375 IMAD.MOV per pair on the very pipe the multiplier is bound by.
 __device__ __noinline__ Fr fr_mulc(const Fr a, const Fr b) { return fr_mul(a, b); }
 __device__ __forceinline__ Fr fr_sqrc(const Fr& a) { return fr_mulc(a, a); }
 
-// acc (17 x 32-bit limbs, one every `stride` words) += a*b as a PLAIN 512-bit product: no Montgomery reduction.
-// Half the multiplier work of fr_mul (64 of its 136 wide multiply-adds); whoever consumes the sum reduces it once
-// (the host, for the round sums: REDC(sum of products) == sum of Montgomery products, exactly).  544 bits hold
-// 2^36 products of values < q.  Out of line for the same reason as fr_mulc.
-#if GKR_ACC_KARA
-__device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr a, const Fr b) {
-    uint32_t P[16];
-    hd_mul_wide_k(a, b, P);  // 48 wide multiply-adds
-    uint32_t w[17];
-#pragma unroll
-    for (int l = 0; l < 17; l++) w[l] = acc[l * stride];
-    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(w[0]) : "r"(P[0]));
-#pragma unroll
-    for (int l = 1; l < 16; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(w[l]) : "r"(P[l]));
-    asm volatile("addc.u32 %0, %0, 0;" : "+r"(w[16]));
-#pragma unroll
-    for (int l = 0; l < 17; l++) acc[l * stride] = w[l];
+// a[0..8) += b[0..8) (+ cin); returns the carry out (0 or 1).  The whole carry chain lives in ONE asm statement and the
+// carry crosses statements in a register, never in the condition code.
+__device__ __forceinline__ uint32_t add8_carry(uint32_t* a, const uint32_t* b) {
+    uint32_t cout;
+    asm("add.cc.u32 %0, %0, %9;\n\t"
+        "addc.cc.u32 %1, %1, %10;\n\t"
+        "addc.cc.u32 %2, %2, %11;\n\t"
+        "addc.cc.u32 %3, %3, %12;\n\t"
+        "addc.cc.u32 %4, %4, %13;\n\t"
+        "addc.cc.u32 %5, %5, %14;\n\t"
+        "addc.cc.u32 %6, %6, %15;\n\t"
+        "addc.cc.u32 %7, %7, %16;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "=r"(cout)
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return cout;
 }
-#else
-__device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr a, const Fr b) {
+__device__ __forceinline__ uint32_t add8_carry_in(uint32_t* a, const uint32_t* b, uint32_t cin) {
+    uint32_t cout, dead;
+    asm("add.cc.u32 %9, %18, 0xffffffff;\n\t"  // sets the carry iff cin == 1
+        "addc.cc.u32 %0, %0, %10;\n\t"
+        "addc.cc.u32 %1, %1, %11;\n\t"
+        "addc.cc.u32 %2, %2, %12;\n\t"
+        "addc.cc.u32 %3, %3, %13;\n\t"
+        "addc.cc.u32 %4, %4, %14;\n\t"
+        "addc.cc.u32 %5, %5, %15;\n\t"
+        "addc.cc.u32 %6, %6, %16;\n\t"
+        "addc.cc.u32 %7, %7, %17;\n\t"
+        "addc.u32 %8, 0, 0;"
+        : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "=r"(cout), "=r"(dead)
+        : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(cin));
+    (void)dead;
+    return cout;
+}
+
+// Plain 512-bit product a*b (no Montgomery reduction) into w[0..16): 64 wide multiply-adds.
+__device__ __forceinline__ void fr_mul_wide(uint32_t (&w)[16], const Fr& a, const Fr& b) {
     uint32_t P[18], Qd[18];
 #pragma unroll
     for (int i = 0; i < 18; i++) P[i] = 0, Qd[i] = 0;
@@ -307,22 +317,57 @@ __device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr
         chain4(S[i], S[i + 1], S[i + 2], S[i + 3], S[i + 4], S[i + 5], S[i + 6], S[i + 7], S[i + 8], a.v[0], a.v[2], a.v[4], a.v[6], bi);
         chain4(T[i + 1], T[i + 2], T[i + 3], T[i + 4], T[i + 5], T[i + 6], T[i + 7], T[i + 8], T[i + 9], a.v[1], a.v[3], a.v[5], a.v[7], bi);
     }
-    // product = P + Qd (< 2^512: limb 16 of the sum is zero); carries ride the condition code from one statement to the
-    // next (nothing between them touches it -- the usual multi-precision idiom)
+    // product = P + Qd (< 2^512: limb 16 of the sum is zero)
+    const uint32_t c = add8_carry(P, Qd);
+    (void)add8_carry_in(P + 8, Qd + 8, c);
+#pragma unroll
+    for (int l = 0; l < 16; l++) w[l] = P[l];
+}
+
+// acc (17 x 32-bit limbs, one every `stride` words) += a*b as a PLAIN 512-bit product: no Montgomery reduction.
+// Half the multiplier work of fr_mul (64 of its 136 wide multiply-adds); whoever consumes the sum reduces it once
+// (the host, for the round sums: REDC(sum of products) == sum of Montgomery products, exactly).  544 bits hold
+// 2^36 products of values < q.
+__device__ __forceinline__ void fr_mul_acc_wide_inl(uint32_t* acc, int stride, const Fr& a, const Fr& b) {
+    uint32_t p[16];
+    fr_mul_wide(p, a, b);
     uint32_t w[17];
 #pragma unroll
     for (int l = 0; l < 17; l++) w[l] = acc[l * stride];
-    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(P[0]) : "r"(Qd[0]));
-#pragma unroll
-    for (int l = 1; l < 16; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(P[l]) : "r"(Qd[l]));
-    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(w[0]) : "r"(P[0]));
-#pragma unroll
-    for (int l = 1; l < 16; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(w[l]) : "r"(P[l]));
-    asm volatile("addc.u32 %0, %0, 0;" : "+r"(w[16]));
+    uint32_t c = add8_carry(w, p);
+    c = add8_carry_in(w + 8, p + 8, c);
+    w[16] += c;
 #pragma unroll
     for (int l = 0; l < 17; l++) acc[l * stride] = w[l];
 }
-#endif
+__device__ __noinline__ void fr_mul_acc_wide(uint32_t* acc, int stride, const Fr a, const Fr b) { fr_mul_acc_wide_inl(acc, stride, a, b); }
+
+// Montgomery reduction of a 512-bit value t < q * 2^256: t * 2^-256 mod q, canonical.  The eight rows of fr_mul without
+// their a*b_i chains (72 wide multiply-adds).  The rows run on t mod 2^256 only: the limbs a chain uses as its carry-out
+// (`top`) then hold nothing but earlier carries and cannot wrap; t >> 256 is added at the end.
+__device__ __forceinline__ Fr fr_redc_wide(const uint32_t (&t)[16]) {
+    uint32_t P[18], Qd[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) P[i] = i < 8 ? t[i] : 0, Qd[i] = 0;
+    const uint32_t q[8] = {FR_Q0, FR_Q1, FR_Q2, FR_Q3, FR_Q4, FR_Q5, FR_Q6, FR_Q7};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t* S = (i & 1) ? Qd : P;
+        uint32_t* T = (i & 1) ? P : Qd;
+        const uint32_t m = fr_mont_m(S[i] + T[i]);
+        chain4(S[i], S[i + 1], S[i + 2], S[i + 3], S[i + 4], S[i + 5], S[i + 6], S[i + 7], S[i + 8], q[0], q[2], q[4], q[6], m);
+        chain4_cin(T[i + 1], T[i + 2], T[i + 3], T[i + 4], T[i + 5], T[i + 6], T[i + 7], T[i + 8], T[i + 9], q[1], q[3], q[5], q[7], m, S[i], T[i]);
+    }
+    uint32_t r[8], hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) r[i] = P[8 + i], hi[i] = t[8 + i];
+    (void)add8_carry(r, Qd + 8);
+    (void)add8_carry(r, hi);  // (t + M*q) / 2^256 < 2q < 2^255: no carry out
+    Fr v;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v.v[i] = r[i];
+    return fr_reduce_once(v);
+}
 
 // x^7 = ((x^2 * x)^2) * x  -- same chain as hash/poseidon.go:129-135 and circuit/gates/cipher.go:37-40
 __device__ __forceinline__ Fr fr_pow7(const Fr& x) {

@@ -14,6 +14,7 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -62,6 +63,10 @@ struct Nccl {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     std::once_flag once;
     bool ok = false;
@@ -75,8 +80,12 @@ struct Nccl {
             CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
             CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
             AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+            Send = (decltype(Send))dlsym(h, "ncclSend");
+            Recv = (decltype(Recv))dlsym(h, "ncclRecv");
+            GroupStart = (decltype(GroupStart))dlsym(h, "ncclGroupStart");
+            GroupEnd = (decltype(GroupEnd))dlsym(h, "ncclGroupEnd");
             GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
-            ok = GetUniqueId && CommInitRank && CommDestroy && AllGather && GetErrorString;
+            ok = GetUniqueId && CommInitRank && CommDestroy && AllGather && Send && Recv && GroupStart && GroupEnd && GetErrorString;
         });
         return ok;
     }
@@ -130,10 +139,11 @@ struct gkrb200_ctx {
     uint32_t* partials_w = nullptr;  // 8 x 17 64-bit limb-column sums of the factored cipher round (zero between launches)
     int max_grid = 0;
 
-    // pinned, device-mapped result slot
+    // pinned, device-mapped result slot: tagged 64-bit words only (see publish_word in kernels.cuh)
     FrRaw* h_result = nullptr;  // [512] (16 KiB: 8 ranks x 8 wide sums x 17 tagged 64-bit words fit)
-    volatile uint32_t* h_flag = nullptr;
     uint32_t seq = 0;
+    FrRaw* d_chal = nullptr;        // [2] challenges delivered to the device by the round kernels' last blocks (leader mode)
+    unsigned int* d_err = nullptr;  // device flag raised when a challenge did not arrive in time
     H::Fr* h_stage = nullptr;  // pinned staging for qprimes/mults uploads [MAX_CLAIMS*(max_bn+1)]
 
     // assignment state
@@ -159,6 +169,37 @@ struct gkrb200_ctx {
     uint8_t* xslot_h(uint32_t tag, int g) const { return x_base + ((size_t)(tag & 1) * (size_t)world + (size_t)g) * XSLOT; }
     uint8_t* xslot_d(uint32_t tag, int g) const { return x_dev + ((size_t)(tag & 1) * (size_t)world + (size_t)g) * XSLOT; }
     bool windowed(int W) const { return W > 1 && use_window; }
+    // One transcript per proof (SURVEY.md section 8e "not sharded: the transcript ... run once, broadcast"): the LEADER rank of the
+    // communicator reads every rank's round sums from the window, runs interpolation + MimcHash and writes the challenge
+    // back into the window as 8 tagged words ([2 parities] x 64 bytes after the sum slots); the last block of EVERY rank's
+    // round kernel polls it and hands it to the next launch through device memory (ChalWait in kernels.cuh).  Follower
+    // ranks enqueue a whole layer of launches and sleep until the leader posts the layer's header (round polynomials,
+    // challenges, final claims: host-only part of the window, one ring entry per layer).
+    int leader = 0;
+    bool replicated_transcript = false;  // GKRB200_OPT_TRANSCRIPT = 1: every rank runs the transcript in lockstep (round 1 behaviour)
+    uint64_t hseq = 0;                   // sequence number of the last layer header posted / consumed
+    bool lead_mode(int W) const { return windowed(W) && !replicated_transcript; }
+    size_t xchal_off() const { return 2 * (size_t)world * XSLOT; }
+    volatile uint64_t* xchal_h(uint32_t tag) const { return (volatile uint64_t*)(x_base + xchal_off() + (size_t)(tag & 1) * 64); }
+    const unsigned long long* xchal_d(uint32_t tag) const { return (const unsigned long long*)(x_dev + xchal_off() + (size_t)(tag & 1) * 64); }
+    struct LayerHeader {
+        volatile uint64_t seq;
+        uint64_t pad[3];
+        H::Fr fin[4];
+        H::Fr challenges[32];
+        H::Fr coeffs[32 * 9];
+    };
+    LayerHeader* xheader(int layer) const { return (LayerHeader*)(x_base + xchal_off() + 256) + layer; }
+    static size_t xwindow_size(int world) { return 2 * (size_t)world * XSLOT + 256 + (size_t)GKRB200_MIMC_LAYERS * sizeof(LayerHeader); }
+    gkr::ChalWait chal_wait(uint32_t tag, int k) const { return gkr::ChalWait{xchal_d(tag), d_chal + (k & 1), d_err, tag}; }
+    void post_challenge(uint32_t tag, const H::Fr& r) const {
+        volatile uint64_t* w = xchal_h(tag);
+        for (int l = 0; l < 8; l++) w[l] = ((uint64_t)tag << 32) | (uint32_t)(r.l[l >> 1] >> (32 * (l & 1)));
+    }
+    int post_header(int layer, const H::Fr* coeffs, size_t n_coeffs, const H::Fr* challenges, int bn, const H::Fr* fin, int n_fin);
+    int wait_header(int layer, H::Fr* coeffs, size_t n_coeffs, H::Fr* challenges, int bn, H::Fr* fin, int n_fin);
+    int carve(size_t new_cap);
+    int cap_bn = 0;  // log2(cap): what unsharded operations on this context can hold
 
     // instrumentation
     gkrb200_stats st{};
@@ -181,8 +222,6 @@ struct gkrb200_ctx {
     int ev_flush();
     void prof_begin(int cls);
     void prof_end();
-    int wait_flag(uint32_t seq);
-    int wait_flag_at(const volatile uint32_t* flag, uint32_t seq);
     int wait_words(uint32_t seq, size_t n_words);
     int wait_words_at(const volatile uint64_t* w, uint32_t seq, size_t n_words);
     int upload(FrRaw* dst, const void* src, size_t n_elems);
@@ -192,11 +231,13 @@ struct gkrb200_ctx {
                  int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out,
                  const H::Fr* trusted_claim = nullptr);
     size_t par8_max_pairs = 8192;  // rounds with at most this many pairs spread one pair over 8 lanes
+    size_t inline_min_pairs = 0;   // one-thread-per-pair rounds with at least this many pairs run the kernel with the inlined multiplier
     bool force_generic = false;  // test hook: run cipher layers through the generic evaluate-at-9-points kernel
-    int exchange_and_fetch(int nacc, int W, uint32_t tag, H::Fr* out);
     int exchange_and_fetch_wide(int nm, int wl, int W, uint32_t tag, H::Fr* out);
     int mle_eval(const FrRaw* table, int bn_total, const H::Fr* point, bool use_shards, H::Fr* out);
     int fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX_FWD]);
+    int residual_enqueue(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, const FrRaw* r_dev, int W, uint32_t* tag_out);
+    int residual_collect(int ntab, size_t lres, int W, uint32_t tag, H::Fr (*tabs)[TAIL_MAX_FWD]);
     int tail_len = TAIL_MAX_FWD;     // option: residual length (entries over all ranks) handed to the host
     int sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn_total, const H::Fr* q, const H::Fr* trusted_claim, const H::Fr& ark, bool use_shards,
                     H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out);
@@ -244,29 +285,6 @@ int gkrb200_ctx::ev_flush() {
         (ctx)->prof_end();                                                         \
     } while (0)
 
-// spin on the mapped flag; bail out if the stream died or after a generous timeout (never hang the box)
-int gkrb200_ctx::wait_flag(uint32_t want) { return wait_flag_at(h_flag, want); }
-int gkrb200_ctx::wait_flag_at(const volatile uint32_t* h_flag, uint32_t want) {
-    const double t0 = now_ms();
-    unsigned spins = 0;
-    while (*h_flag != want) {
-        _mm_pause();
-        if ((++spins & 0xfff) == 0) {
-            cudaError_t q = cudaStreamQuery(stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(GKRB200_ERR_CUDA, "stream error while waiting: %s", cudaGetErrorString(q));
-            if (q == cudaSuccess && *h_flag != want && h_flag == this->h_flag) {
-                // own result slot and the stream drained: give the write a moment to land, then give up
-                for (int i = 0; i < 100000 && *h_flag != want; i++) _mm_pause();
-                if (*h_flag != want) return fail(GKRB200_ERR_CUDA, "device finished without publishing result %u (have %u)", want, *h_flag);
-            }
-            if (now_ms() - t0 > 60000.0) return fail(GKRB200_ERR_CUDA, "timeout waiting for device result");
-        }
-    }
-    std::atomic_thread_fence(std::memory_order_acquire);
-    st.wait_ms += now_ms() - t0;
-    return 0;
-}
-
 // spin until every tagged 64-bit word of h_result carries `want` in its upper half (see publish_word in kernels.cuh)
 int gkrb200_ctx::wait_words(uint32_t want, size_t n_words) { return wait_words_at((const volatile uint64_t*)h_result, want, n_words); }
 int gkrb200_ctx::wait_words_at(const volatile uint64_t* w, uint32_t want, size_t n_words) {
@@ -310,6 +328,10 @@ static inline int grid_for(size_t work_items, int block, int max_grid) {
 static constexpr int CF_BLOCK = 128;  // PAR == 8 kernels
 static constexpr int CF_BLOCK1 = 128; // PAR == 1 kernels: 7-8 accumulators x 17 limbs x 128 threads = 61-70 KB of shared memory per block (64-thread blocks measured 30 % slower)
 static constexpr int CF_MINB1 = 3;    // -> 3 blocks (12 warps) per SM
+#ifndef GKR_CF_MINB_INL
+#define GKR_CF_MINB_INL 4
+#endif
+static constexpr int CF_MINB_INL = GKR_CF_MINB_INL;  // register cap of the inlined-multiplier build (65536 / (128 * MINB)): 3 blocks are resident (shared memory), the rest of the register file stays free for the small kernels of other proofs in flight
 static constexpr int CF_MINB8 = 4;
 static constexpr int CF_WL1 = 17;   // limbs per accumulator, PAR == 1 (plain 512-bit products summed)
 static constexpr int CF_WL8 = 9;    // PAR == 8 (reduced products summed)
@@ -317,21 +339,26 @@ static constexpr size_t CF_SMEM_PAR8 = (8 * 9 + (CF_BLOCK / 32) * 8 * 9 + (CF_BL
 static inline size_t cf_smem(int nm, bool par8) { return par8 ? CF_SMEM_PAR8 : (size_t)nm * CF_WL1 * CF_BLOCK1 * 4; }
 
 typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
-static cf_kernel_t cf_kernel(bool fold, int nm, bool par8) {
+// variant: 0 = one thread per pair, multiplier inlined (big rounds); 1 = eight lanes per pair (small rounds);
+//          2 = one thread per pair, multiplier out of line (mid-size rounds / A-B reference)
+enum { CF_V_INL = 0, CF_V_PAR8 = 1, CF_V_CALL = 2 };
+static cf_kernel_t cf_kernel(bool fold, int nm, int variant) {
     using namespace gkr;
-#define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK1, CF_MINB1>
-#define CF_K8(F, N) k_round_cf<F, N, 8, CF_BLOCK, CF_MINB8>
-    static const cf_kernel_t tab[2][2][2] = {{{CF_K1(false, 7), CF_K8(false, 7)}, {CF_K1(false, 8), CF_K8(false, 8)}},
-                                             {{CF_K1(true, 7), CF_K8(true, 7)}, {CF_K1(true, 8), CF_K8(true, 8)}}};
+#define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK1, CF_MINB_INL, true>
+#define CF_K8(F, N) k_round_cf<F, N, 8, CF_BLOCK, CF_MINB8, false>
+#define CF_KC(F, N) k_round_cf<F, N, 1, CF_BLOCK1, CF_MINB1, false>
+    static const cf_kernel_t tab[2][2][3] = {{{CF_K1(false, 7), CF_K8(false, 7), CF_KC(false, 7)}, {CF_K1(false, 8), CF_K8(false, 8), CF_KC(false, 8)}},
+                                             {{CF_K1(true, 7), CF_K8(true, 7), CF_KC(true, 7)}, {CF_K1(true, 8), CF_K8(true, 8), CF_KC(true, 8)}}};
 #undef CF_K1
 #undef CF_K8
-    return tab[fold ? 1 : 0][nm == 8 ? 1 : 0][par8 ? 1 : 0];
+#undef CF_KC
+    return tab[fold ? 1 : 0][nm == 8 ? 1 : 0][variant];
 }
 static int set_cf_attrs() {
     for (int f = 0; f < 2; f++)
         for (int n = 7; n <= 8; n++)
-            for (int p = 0; p < 2; p++)
-                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, p), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem(n, p)));
+            for (int v = 0; v < 3; v++)
+                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem(n, v == CF_V_PAR8)));
     return 0;
 }
 
@@ -394,7 +421,6 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
 static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
     c->device = device;
     c->max_bn = max_bn;
-    c->cap = (size_t)1 << max_bn;
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) {
@@ -408,36 +434,12 @@ static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    const size_t half = c->cap / 2 > 0 ? c->cap / 2 : 1;
-    const int nsmall = (max_bn + 1) / 2;
-    const size_t small = (size_t)1 << nsmall;
-    size_t total = 93 * c->cap + c->cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
-                   (size_t)c->max_grid * MAX_EV + 64 + 8 * 64 + 3 * 32 + 64 + ((size_t)c->n_sm * 8 * 8 * 17 * 4 + 31) / 32;
-    cudaError_t me = cudaMalloc(&c->arena, total * sizeof(FrRaw));
-    if (me != cudaSuccess) {
-        c->arena = nullptr;
-        return fail(GKRB200_ERR_OOM, "cudaMalloc of %.2f GiB arena failed: %s", total * 32.0 / (1 << 30), cudaGetErrorString(me));
-    }
-    FrRaw* p = c->arena;
-    c->layers = p; p += 93 * c->cap;
-    c->eq = p; p += c->cap;
-    for (int i = 0; i < 3; i++) { c->scratch[i] = p; p += half; }
-    c->hi = p; p += MAX_CLAIMS * small;
-    c->lo = p; p += MAX_CLAIMS * small;
-    c->d_q = p; p += (size_t)MAX_CLAIMS * (max_bn + 1);
-    c->d_mults = p; p += MAX_CLAIMS;
-    c->partials = p; p += (size_t)c->max_grid * MAX_EV;
-    c->d_local = p; p += 64;
-    c->d_all = p; p += 8 * 64;
-    c->d_resid = p; p += 3 * 32;
-    c->partials_w = (uint32_t*)p; p += ((size_t)c->n_sm * 8 * 8 * 17 * 4 + 31) / 32;
-    CUDA_TRY(cudaMemset(c->partials_w, 0, 8 * 17 * 8));
-    CUDA_TRY(cudaMalloc(&c->ticket, 64));
-    CUDA_TRY(cudaMemset(c->ticket, 0, 64));
-    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 512 * sizeof(FrRaw) + 64, cudaHostAllocMapped));
-    memset(c->h_result, 0, 512 * sizeof(FrRaw) + 64);
-    c->h_flag = (volatile uint32_t*)(c->h_result + 512);
-    *c->h_flag = 0;
+    TRY(c->carve((size_t)1 << max_bn));
+    CUDA_TRY(cudaMalloc(&c->ticket, 128));
+    CUDA_TRY(cudaMemset(c->ticket, 0, 128));
+    c->d_err = c->ticket + 16;
+    CUDA_TRY(cudaHostAlloc((void**)&c->h_result, 512 * sizeof(FrRaw), cudaHostAllocMapped));
+    memset(c->h_result, 0, 512 * sizeof(FrRaw));
     CUDA_TRY(cudaHostAlloc((void**)&c->h_stage, (size_t)MAX_CLAIMS * (max_bn + 2) * sizeof(H::Fr), cudaHostAllocDefault));
     // opt in to the dynamic shared memory the round kernels need
     const int smem9 = 9 * 9 * ROUND_BLOCK * 4, smem3 = 3 * 9 * ROUND_BLOCK * 4;
@@ -448,9 +450,52 @@ static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
     TRY(set_cf_attrs());
     for (int n = 7; n <= 8; n++) {  // resident blocks per SM of the PAR == 1 kernels (shared-memory bound): the grid is exactly one wave
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cf_kernel(true, n, false), CF_BLOCK1, cf_smem(n, false)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cf_kernel(true, n, CF_V_INL), CF_BLOCK1, cf_smem(n, false)));
         c->cf_blocks_per_sm1[n - 7] = nb > 0 ? nb : 1;
     }
+    return 0;
+}
+
+static void comm_teardown(gkrb200_ctx* c);
+// (Re)builds the device arena for tables of `new_cap` entries: one allocation, carved into the 93 layer tables, the eq table,
+// the ping-pong scratch and the small per-layer buffers.  A sharded context holds 1/world of every table, so
+// gkrb200_comm_init calls this again with cap = 2^max_bn / world (the arena must shrink with the shard).
+int gkrb200_ctx::carve(size_t new_cap) {
+    if (arena) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        CUDA_TRY(cudaFree(arena));
+        arena = nullptr;
+    }
+    cap = new_cap;
+    cap_bn = 0;
+    while (((size_t)1 << (cap_bn + 1)) <= cap) cap_bn++;
+    const size_t half = cap / 2 > 0 ? cap / 2 : 1;
+    const int nsmall = (max_bn + 1) / 2;
+    const size_t small = (size_t)1 << nsmall;
+    const size_t pw_elems = ((size_t)8 * 17 * 8 + 31) / 32;  // 8 x 17 64-bit limb-column sums
+    size_t total = 93 * cap + cap + 3 * half + 2 * MAX_CLAIMS * small + (size_t)MAX_CLAIMS * (max_bn + 1) + MAX_CLAIMS +
+                   (size_t)max_grid * MAX_EV + 64 + 8 * 64 + 3 * 32 + 64 + pw_elems + 2;
+    cudaError_t me = cudaMalloc(&arena, total * sizeof(FrRaw));
+    if (me != cudaSuccess) {
+        arena = nullptr;
+        return fail(GKRB200_ERR_OOM, "cudaMalloc of %.2f GiB arena failed: %s", total * 32.0 / (1 << 30), cudaGetErrorString(me));
+    }
+    FrRaw* p = arena;
+    layers = p; p += 93 * cap;
+    eq = p; p += cap;
+    for (int i = 0; i < 3; i++) { scratch[i] = p; p += half; }
+    hi = p; p += MAX_CLAIMS * small;
+    lo = p; p += MAX_CLAIMS * small;
+    d_q = p; p += (size_t)MAX_CLAIMS * (max_bn + 1);
+    d_mults = p; p += MAX_CLAIMS;
+    partials = p; p += (size_t)max_grid * MAX_EV;
+    d_local = p; p += 64;
+    d_all = p; p += 8 * 64;
+    d_resid = p; p += 3 * 32;
+    partials_w = (uint32_t*)p; p += pw_elems;
+    d_chal = p; p += 2;
+    CUDA_TRY(cudaMemset(partials_w, 0, 8 * 17 * 8));
+    bn = -1;  // whatever assignment the old arena held is gone
     return 0;
 }
 
@@ -458,11 +503,7 @@ extern "C" void gkrb200_free(gkrb200_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    if (c->x_base) {
-        cudaHostUnregister(c->x_base);
-        munmap(c->x_base, c->x_size);
-    }
+    comm_teardown(c);
     for (auto& e : c->ev_pool) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -482,16 +523,40 @@ extern "C" int gkrb200_comm_unique_id(uint8_t id_out[128]) {
     memcpy(id_out, id.internal, 128);
     return 0;
 }
+// releases the communicator and the exchange window of a context (comm_init on a context that already has them, and free)
+static void comm_teardown(gkrb200_ctx* c) {
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    c->comm = nullptr;
+    if (c->x_base) {
+        cudaHostUnregister(c->x_base);
+        munmap(c->x_base, c->x_size);
+    }
+    c->x_base = c->x_dev = nullptr;
+    c->x_size = 0;
+    c->use_window = false;
+}
+
 extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint8_t uid[128]) {
     if (!c || world < 1 || world > 8 || (world & (world - 1)) || rank < 0 || rank >= world)
         return fail(GKRB200_ERR_ARG, "bad rank/world %d/%d (world must be a power of two <= 8)", rank, world);
+    if (world > 1 && !uid) return fail(GKRB200_ERR_ARG, "null nccl unique id");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    comm_teardown(c);  // a second comm_init on the same context replaces the first communicator
     c->rank = rank;
     c->world = world;
+    c->leader = 0;
     c->log_world = 0;
     while ((1 << c->log_world) < world) c->log_world++;
+    // a sharded context holds 1/world of every table: shrink (or restore) the arena accordingly.  64 entries is the floor
+    // (batches of at most `world` hashes run unsharded, and tiny sharded batches stage the full inputs).
+    {
+        size_t want = (size_t)1 << c->max_bn;
+        if (world > 1) want = std::max<size_t>(want >> c->log_world, std::min<size_t>(want, 64));
+        if (want != c->cap) TRY(c->carve(want));
+    }
     if (world == 1) return 0;
     if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl.so.2 (or a symbol is missing)");
-    CUDA_TRY(cudaSetDevice(c->device));
     ncclUniqueId id;
     memcpy(id.internal, uid, 128);
     // ---- exchange window (see gkrb200_ctx): opened by every rank BEFORE the NCCL rendezvous, unlinked by rank 0 after it
@@ -501,31 +566,40 @@ extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint
         for (int i = 0; i < 128; i++) h = (h ^ uid[i]) * 1099511628211ull;
         snprintf(name, sizeof name, "/gkrb200-%016llx", (unsigned long long)h);
     }
-    const size_t xsize = 2 * (size_t)world * gkrb200_ctx::XSLOT;
-    int fd = -1;
+    const size_t xsize = gkrb200_ctx::xwindow_size(world);
+    // every exit path below closes the descriptor and (rank 0) unlinks the segment
+    struct Shm {
+        int fd = -1;
+        const char* name = nullptr;
+        bool owner = false;
+        ~Shm() {
+            if (fd >= 0) close(fd);
+            if (owner && name) shm_unlink(name);
+        }
+    } shm;
+    shm.name = name;
     if (rank == 0) {
         shm_unlink(name);
-        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
-        if (fd >= 0 && ftruncate(fd, (off_t)xsize) != 0) {  // ftruncate zero-fills: tag 0 is never used by an exchange
-            close(fd);
-            fd = -1;
+        shm.fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        shm.owner = shm.fd >= 0;
+        if (shm.fd >= 0 && ftruncate(shm.fd, (off_t)xsize) != 0) {  // ftruncate zero-fills: tag 0 is never used by an exchange
+            close(shm.fd);
+            shm.fd = -1;
         }
     }
     // NCCL's rendezvous doubles as the barrier "rank 0 has created the segment"
     NCCL_TRY(g_nccl.CommInitRank(&c->comm, world, id, rank));
     if (rank != 0) {
-        fd = shm_open(name, O_RDWR, 0600);
+        shm.fd = shm_open(name, O_RDWR, 0600);
         struct stat sb;
-        if (fd >= 0 && (fstat(fd, &sb) != 0 || (size_t)sb.st_size != xsize)) {
-            close(fd);
-            fd = -1;
+        if (shm.fd >= 0 && (fstat(shm.fd, &sb) != 0 || (size_t)sb.st_size != xsize)) {
+            close(shm.fd);
+            shm.fd = -1;
         }
     }
     uint8_t ok = 0;
-    void* base = MAP_FAILED;
-    if (fd >= 0) {
-        base = mmap(nullptr, xsize, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
-        close(fd);
+    if (shm.fd >= 0) {
+        void* base = mmap(nullptr, xsize, PROT_READ | PROT_WRITE, MAP_SHARED, shm.fd, 0);
         if (base != MAP_FAILED) {
             void* dev = nullptr;
             if (cudaHostRegister(base, xsize, cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess &&
@@ -546,12 +620,20 @@ extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint
     uint8_t oks[8] = {0};
     CUDA_TRY(cudaMemcpyAsync(oks, c->d_all, (size_t)world, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (rank == 0) shm_unlink(name);
     bool all_ok = true;
     for (int g = 0; g < world; g++) all_ok = all_ok && oks[g] == 1;
     c->use_window = all_ok;
     c->xseq = 0;
+    c->hseq = 0;
     if (!all_ok && getenv("GKRB200_VERBOSE")) fprintf(stderr, "gkrb200: rank %d: no shared exchange window (ok=%d), using NCCL all-gather\n", rank, (int)ok);
+    return 0;
+}
+
+// Which rank runs the transcript of this communicator's proofs (default 0).  Set identically on every rank; with several
+// proofs in flight (one communicator each) rotating the leader spreads the host work over the ranks' processes.
+extern "C" int gkrb200_comm_set_leader(gkrb200_ctx* c, int leader_rank) {
+    if (!c || leader_rank < 0 || leader_rank >= c->world) return fail(GKRB200_ERR_ARG, "leader rank %d out of range", leader_rank);
+    c->leader = leader_rank;
     return 0;
 }
 
@@ -566,38 +648,75 @@ static int assign_common(gkrb200_ctx* c, size_t n_local) {
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
-static int check_n(gkrb200_ctx* c, size_t n, int* bn_out) {
+// shards: the call splits the table over the ranks of the communicator (the assignment); otherwise it must fit this rank's arena
+static int check_n(gkrb200_ctx* c, size_t n, int* bn_out, bool shards = false) {
+    *bn_out = 0;
     if (!c) return fail(GKRB200_ERR_ARG, "null context");
     if (n == 0 || (n & (n - 1))) return fail(GKRB200_ERR_ARG, "table size %zu is not a power of two", n);
     int bn = 0;
     while (((size_t)1 << bn) < n) bn++;
-    if (bn > c->max_bn) return fail(GKRB200_ERR_OOM, "batch 2^%d exceeds the context capacity 2^%d", bn, c->max_bn);
+    const int limit = (shards && c->world > 1 && bn > c->log_world) ? std::min(c->max_bn, c->cap_bn + c->log_world) : c->cap_bn;
+    if (bn > limit) return fail(GKRB200_ERR_OOM, "batch 2^%d exceeds the context capacity 2^%d", bn, limit);
     *bn_out = bn;
     return 0;
 }
 
-extern "C" int gkrb200_mimc_assign(gkrb200_ctx* c, const uint64_t* key, const uint64_t* msg, size_t n, uint64_t* out93) {
-    int bn;
-    TRY(check_n(c, n, &bn));
-    if (!key || !msg) return fail(GKRB200_ERR_ARG, "null input table");
-    CUDA_TRY(cudaSetDevice(c->device));
+// Host key/msg (full tables, Go layout) -> this rank's layer-0 / layer-1 tables.  Sharded: the rank uploads only ITS
+// contiguous 1/world slice of each table over PCIe (total H2D = one copy of the inputs, however many GPUs), de-interleaves it
+// by owner (entry i belongs to rank i mod world) and the ranks swap the blocks with one grouped NCCL send/recv over NVLink --
+// the only bandwidth-relevant transfer between GPUs on this path.
+static int stage_inputs(gkrb200_ctx* c, const uint64_t* key, const uint64_t* msg, size_t n, int bn) {
     c->sharded = c->world > 1 && bn > c->log_world;
     c->bn = bn;
     if (!c->sharded) {
         c->n_local = n;
         TRY(c->upload(c->slot(0), key, n));
         TRY(c->upload(c->slot(1), msg, n));
-    } else {
-        // every rank receives the full tables and keeps entries {i : i mod world == rank}
-        c->n_local = n / (size_t)c->world;
-        FrRaw* tmp_key = c->eq;          // cap entries
-        FrRaw* tmp_msg = c->scratch[0];  // 3*cap/2 contiguous entries
-        TRY(c->upload(tmp_key, key, n));
-        TRY(c->upload(tmp_msg, msg, n));
-        const int grid = grid_for(c->n_local, 256, c->n_sm * 8);
-        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_key, c->slot(0), c->n_local, c->world, c->rank);
-        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_msg, c->slot(1), c->n_local, c->world, c->rank);
+        return 0;
     }
+    const size_t W = (size_t)c->world, nl = n / W;
+    c->n_local = nl;
+    FrRaw* st_key = c->eq;          // cap entries
+    FrRaw* st_msg = c->scratch[0];  // 3*cap/2 contiguous entries
+    if (nl >= W && nl % W == 0) {
+        const size_t blk = nl / W;
+        TRY(c->upload(st_key, key + 4 * (size_t)c->rank * nl, nl));
+        TRY(c->upload(st_msg, msg + 4 * (size_t)c->rank * nl, nl));
+        FrRaw* snd_key = c->slot(3);  // layers 3 and 4 are free until the assignment kernel runs
+        FrRaw* snd_msg = c->slot(4);
+        const int grid = grid_for(nl, 256, c->n_sm * 8);
+        LAUNCH(c, KC_STAGING, gkr::k_destripe, grid, 256, 0, st_key, snd_key, nl, (int)W);
+        LAUNCH(c, KC_STAGING, gkr::k_destripe, grid, 256, 0, st_msg, snd_msg, nl, (int)W);
+        CUDA_TRY(cudaGetLastError());
+        const double t0 = now_ms();
+        NCCL_TRY(g_nccl.GroupStart());
+        for (size_t peer = 0; peer < W; peer++) {
+            NCCL_TRY(g_nccl.Send(snd_key + peer * blk, blk * sizeof(FrRaw), ncclUint8, (int)peer, c->comm, c->stream));
+            NCCL_TRY(g_nccl.Recv(c->slot(0) + peer * blk, blk * sizeof(FrRaw), ncclUint8, (int)peer, c->comm, c->stream));
+            NCCL_TRY(g_nccl.Send(snd_msg + peer * blk, blk * sizeof(FrRaw), ncclUint8, (int)peer, c->comm, c->stream));
+            NCCL_TRY(g_nccl.Recv(c->slot(1) + peer * blk, blk * sizeof(FrRaw), ncclUint8, (int)peer, c->comm, c->stream));
+        }
+        NCCL_TRY(g_nccl.GroupEnd());
+        c->st.comm_ms += now_ms() - t0;
+        c->st.launches_total++;
+        c->st.launches[KC_STAGING]++;
+        return 0;
+    }
+    // tiny sharded batches (n < world^2): every rank stages the full tables and keeps entries {i : i mod world == rank}
+    TRY(c->upload(st_key, key, n));
+    TRY(c->upload(st_msg, msg, n));
+    const int grid = grid_for(nl, 256, c->n_sm * 8);
+    LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, st_key, c->slot(0), nl, c->world, c->rank);
+    LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, st_msg, c->slot(1), nl, c->world, c->rank);
+    return 0;
+}
+
+extern "C" int gkrb200_mimc_assign(gkrb200_ctx* c, const uint64_t* key, const uint64_t* msg, size_t n, uint64_t* out93) {
+    int bn;
+    TRY(check_n(c, n, &bn, true));
+    if (!key || !msg) return fail(GKRB200_ERR_ARG, "null input table");
+    CUDA_TRY(cudaSetDevice(c->device));
+    TRY(stage_inputs(c, key, msg, n, bn));
     TRY(assign_common(c, c->n_local));
     if (out93) {
         CUDA_TRY(cudaMemcpyAsync(out93, c->slot(93), c->n_local * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
@@ -609,7 +728,7 @@ extern "C" int gkrb200_mimc_assign(gkrb200_ctx* c, const uint64_t* key, const ui
 
 extern "C" int gkrb200_mimc_assign_device(gkrb200_ctx* c, const void* d_key, const void* d_msg, size_t n) {
     int bn;
-    TRY(check_n(c, n, &bn));
+    TRY(check_n(c, n, &bn, true));
     if (!d_key || !d_msg) return fail(GKRB200_ERR_ARG, "null input table");
     CUDA_TRY(cudaSetDevice(c->device));
     c->sharded = c->world > 1 && bn > c->log_world;
@@ -656,35 +775,6 @@ int gkrb200_ctx::build_eq(const H::Fr* qprimes, size_t n_q, int bnl, const H::Fr
     LAUNCH(this, cls, gkr::k_eq_expand, grid, gkr::EQX_BLOCK, 0, hi, lo, nh, nl, (int)n_q, out, n);
     CUDA_TRY(cudaGetLastError());
     // the staging buffer is reused by the next call: make sure the copies above are done
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ multi-GPU exchange
-// Single GPU: the kernel already published into h_result.  Sharded, exchange window (default): every rank's kernel
-// published its partial sums + flag into its own slot of the window; wait for all W flags and add.  Sharded, NCCL
-// (GKRB200_OPT_EXCHANGE = 1): all-gather the per-rank partials over NVLink, sum them on the device and publish.
-int gkrb200_ctx::exchange_and_fetch(int nacc, int W, uint32_t tag, H::Fr* out) {
-    if (windowed(W)) {
-        for (int g = 0; g < W; g++) TRY(wait_flag_at((const volatile uint32_t*)(xslot_h(tag, g) + XSLOT_DATA), tag));
-        for (int k = 0; k < nacc; k++) {
-            H::Fr s = ((const H::Fr*)xslot_h(tag, 0))[k];
-            for (int g = 1; g < W; g++) s = H::add(s, ((const H::Fr*)xslot_h(tag, g))[k]);
-            out[k] = s;
-        }
-        st.d2h_bytes += ((size_t)nacc * sizeof(H::Fr) + 4) * (size_t)W;
-        return 0;
-    }
-    if (W > 1) {
-        const double t0 = now_ms();
-        NCCL_TRY(g_nccl.AllGather(d_local, d_all, (size_t)nacc * sizeof(FrRaw), ncclUint8, comm, stream));
-        st.launches_total++;
-        st.launches[KC_MISC]++;
-        gkr::k_sum_ranks<<<1, 32, 0, stream>>>(d_all, world, nacc, h_result, h_flag, tag);
-        st.comm_ms += now_ms() - t0;
-    }
-    TRY(wait_flag(tag));
-    memcpy(out, (const void*)h_result, (size_t)nacc * sizeof(H::Fr));
-    st.d2h_bytes += (size_t)nacc * sizeof(H::Fr) + 4;
     return 0;
 }
 
@@ -763,9 +853,12 @@ static void host_tail(const H::Lagrange& lagrange, H::Fr* te, H::Fr* t0v, H::Fr*
 }
 
 // Residual tables for the host tail.  cur[t] (t < ntab) are this rank's device tables; when folded_by_r they have length
-// 2*lres and are folded once more with r (the last device challenge), otherwise they have length lres and are taken as is.
-// tabs[t][0 .. lres*W) receives the global residual table: entry j*W + g = rank g's entry j (strided sharding).
-int gkrb200_ctx::fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX]) {
+// 2*lres and are folded once more with the last device challenge (r, or *r_dev when the challenge lives in device memory),
+// otherwise they have length lres and are taken as is.  residual_enqueue only ENQUEUES the device work (and, through the
+// window, the publication of this rank's entries under a fresh exchange tag); residual_collect waits for every rank's entries:
+// tabs[t][j*W + g] = rank g's entry j (strided sharding).
+int gkrb200_ctx::residual_enqueue(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, const FrRaw* r_dev, int W,
+                                  uint32_t* tag_out) {
     if (folded_by_r) {
         gkr::FoldArgs f{};
         f.n_tables = ntab;
@@ -775,19 +868,28 @@ int gkrb200_ctx::fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, 
         }
         f.half = lres;
         memcpy(&f.r, &r, 32);
+        f.r_dev = r_dev;
         LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 128, 0, f);
     } else {
         for (int i = 0; i < ntab; i++)
             CUDA_TRY(cudaMemcpyAsync(d_resid + (size_t)i * lres, cur[i], lres * sizeof(FrRaw), cudaMemcpyDeviceToDevice, stream));
     }
-    const size_t per_rank = (size_t)ntab * lres;
+    *tag_out = 0;
     if (windowed(W)) {
         // every rank publishes its residual entries (tagged 32-bit limbs) into its slot of the exchange window
         const uint32_t tag = ++xseq;
-        const int n_limbs = (int)(per_rank * 8);
+        const int n_limbs = (int)((size_t)ntab * lres * 8);
         LAUNCH(this, KC_MISC, gkr::k_publish_tagged, 1, 256, 0, (const uint32_t*)d_resid, n_limbs, (unsigned long long*)xslot_d(tag, rank), tag);
-        CUDA_TRY(cudaGetLastError());
-        for (int g = 0; g < W; g++) TRY(wait_words_at((const volatile uint64_t*)xslot_h(tag, g), tag, (size_t)n_limbs));
+        *tag_out = tag;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+int gkrb200_ctx::residual_collect(int ntab, size_t lres, int W, uint32_t tag, H::Fr (*tabs)[TAIL_MAX]) {
+    const size_t per_rank = (size_t)ntab * lres;
+    if (windowed(W)) {
+        const size_t n_limbs = per_rank * 8;
+        for (int g = 0; g < W; g++) TRY(wait_words_at((const volatile uint64_t*)xslot_h(tag, g), tag, n_limbs));
         st.d2h_bytes += per_rank * (size_t)W * sizeof(FrRaw);
         for (int g = 0; g < W; g++) {
             const volatile uint64_t* w = (const volatile uint64_t*)xslot_h(tag, g);
@@ -818,10 +920,57 @@ int gkrb200_ctx::fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, 
             for (size_t j = 0; j < lres; j++) tabs[t][j * (size_t)W + g] = h_stage[((size_t)g * ntab + t) * lres + j];
     return 0;
 }
+int gkrb200_ctx::fetch_residual(const FrRaw* const* cur, int ntab, size_t lres, bool folded_by_r, const H::Fr& r, int W, H::Fr (*tabs)[TAIL_MAX]) {
+    uint32_t tag;
+    TRY(residual_enqueue(cur, ntab, lres, folded_by_r, r, nullptr, W, &tag));
+    return residual_collect(ntab, lres, W, tag, tabs);
+}
+
+// ---- layer headers (leader mode): the leader posts what the followers need to stay in step and to assemble the same proof
+int gkrb200_ctx::post_header(int layer, const H::Fr* coeffs, size_t n_coeffs, const H::Fr* challenges, int bn_, const H::Fr* fin, int n_fin) {
+    LayerHeader* h = xheader(layer);
+    if (n_coeffs > 32 * 9 || bn_ > 32 || n_fin > 4) return fail(GKRB200_ERR_STATE, "internal: layer header overflow");
+    if (n_coeffs) memcpy(h->coeffs, coeffs, n_coeffs * sizeof(H::Fr));
+    if (bn_) memcpy(h->challenges, challenges, (size_t)bn_ * sizeof(H::Fr));
+    memcpy(h->fin, fin, (size_t)n_fin * sizeof(H::Fr));
+    std::atomic_thread_fence(std::memory_order_release);
+    h->seq = ++hseq;
+    return 0;
+}
+// Followers sleep here (they have nothing to compute): short naps instead of a spin, so a proof in flight costs ONE host core
+// (its leader's), not one per rank.
+int gkrb200_ctx::wait_header(int layer, H::Fr* coeffs, size_t n_coeffs, H::Fr* challenges, int bn_, H::Fr* fin, int n_fin) {
+    LayerHeader* h = xheader(layer);
+    const uint64_t want = ++hseq;
+    const double t0 = now_ms();
+    unsigned naps = 0;
+    while (h->seq != want) {
+        struct timespec ts = {0, 20000};  // 20 us
+        nanosleep(&ts, nullptr);
+        if ((++naps & 0x3ff) == 0) {
+            cudaError_t q = cudaStreamQuery(stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(GKRB200_ERR_CUDA, "stream error while waiting for the leader: %s", cudaGetErrorString(q));
+            if (now_ms() - t0 > 60000.0) return fail(GKRB200_ERR_COMM, "timeout waiting for the leader's header of layer %d (have %llu, want %llu)", layer,
+                                                     (unsigned long long)h->seq, (unsigned long long)want);
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (n_coeffs) memcpy(coeffs, h->coeffs, n_coeffs * sizeof(H::Fr));
+    if (bn_) memcpy(challenges, h->challenges, (size_t)bn_ * sizeof(H::Fr));
+    memcpy(fin, h->fin, (size_t)n_fin * sizeof(H::Fr));
+    st.follow_wait_ms += now_ms() - t0;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------ sumcheck.Prove
 // x0/x1: device tables of this rank (n_local = 2^(bn_total - log_world) entries when use_shards), never modified.
 // qprimes: n_q * bn_total.  Returns bn_total*(nev) coefficients, bn_total challenges, 1+arity final claims.
+//
+// Two drivers share the code below.  LOCKSTEP (single GPU, or GKRB200_OPT_TRANSCRIPT = 1): launch round k, wait for its sums,
+// run the transcript, pass r_k to launch k+1 by value.  LEADER MODE (sharded, default): every rank enqueues ALL device rounds
+// of the sumcheck up front -- round k+1 reads r_k from device memory, where the last block of round k put it after polling
+// the window (ChalWait) -- and only the communicator's leader rank runs the transcript loop; followers return right after
+// enqueueing (outputs untouched) and pick the results up from the layer header.
 int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr* qprimes, size_t n_q, const H::Fr* claims, size_t n_claims,
                           int gate, const H::Fr& ark, bool use_shards, H::Fr* proof_out, H::Fr* challenges_out, H::Fr* final_out,
                           const H::Fr* trusted_claim) {
@@ -835,6 +984,7 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
     const int nev = gate == gkr::GATE_CIPHER ? 9 : 3;
     const int nin = gate == gkr::GATE_CIPHER ? 2 : 1;
     const size_t n_local = (size_t)1 << bnl;
+    const bool lead = lead_mode(W), am_leader = !lead || rank == leader;
 
     // ---- makeEqTable (sumcheck/prover.go:102-144)
     std::vector<H::Fr> mults;
@@ -844,7 +994,7 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         have_mults = true;
         if (n_claims >= 1 && n_q > 1) {
             const double t0 = now_ms();
-            const H::Fr rho = H::mimc_hash(claims, n_claims);  // prover.go:128
+            const H::Fr rho = H::mimc_hash(claims, n_claims);  // prover.go:128 (once per sumcheck; every rank holds the claims)
             st.transcript_ms += now_ms() - t0;
             H::Fr m = rho;
             for (size_t j = 1; j < n_q; j++) {
@@ -888,7 +1038,8 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
     int tail_bits = 0;
     while (((size_t)2 << tail_bits) * (size_t)W <= (size_t)tail_len && tail_bits < bnl) tail_bits++;
     const int kdev = bnl - tail_bits;
-    for (int k = 0; k < kdev; k++) {
+    uint32_t tags[32];
+    auto launch_round = [&](int k) -> int {
         gkr::RoundArgs a{};
         const bool do_fold = k > 0;
         const size_t half = len / (do_fold ? 4 : 2);
@@ -898,13 +1049,15 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         }
         a.half = half;
         memcpy(&a.r, &r, 32);
+        a.r_dev = (lead && do_fold) ? d_chal + ((k - 1) & 1) : nullptr;
         memcpy(&a.ark, &ark, 32);
         const uint32_t tag = windowed(W) ? ++xseq : ++seq;
+        tags[k] = tag;
         a.red.partials = partials;
         a.red.ticket = ticket;
-        a.red.result = windowed(W) ? (FrRaw*)xslot_d(tag, rank) : (W > 1 ? d_local : h_result);
-        a.red.flag = windowed(W) ? (volatile uint32_t*)(xslot_d(tag, rank) + XSLOT_DATA) : (W > 1 ? nullptr : h_flag);
+        a.red.result = windowed(W) ? (unsigned long long*)xslot_d(tag, rank) : (W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result);
         a.red.seq = tag;
+        a.red.chal = lead ? chal_wait(tag, k) : gkr::ChalWait{nullptr, nullptr, nullptr, 0};
         const int grid = grid_for(half, ROUND_BLOCK, max_grid);
         const size_t smem = (size_t)nev * 9 * ROUND_BLOCK * 4;
         if (gate == gkr::GATE_CIPHER) {
@@ -923,19 +1076,38 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
             for (int i = 0; i < 3; i++) cur[i] = dstp[i];
             len /= 2;
         }
-        TRY(exchange_and_fetch(nev, W, tag, evals));
+        return 0;
+    };
+    auto transcript_round = [&](int k) -> int {
+        TRY(exchange_and_fetch_wide(nev, 9, W, tags[k], evals));
         const double t0 = now_ms();
         H::Fr* coeffs = proof_out + (size_t)k * nev;
         lagrange.interpolate(evals, nev, coeffs);  // poly/lagrange.go:96
         r = H::mimc_hash(coeffs, nev);             // common/challenge.go:10
         challenges_out[k] = r;
+        if (lead) post_challenge(tags[k], r);
         st.transcript_ms += now_ms() - t0;
         st.rounds++;
+        return 0;
+    };
+    uint32_t rtag = 0;
+    const size_t lres = (size_t)1 << tail_bits;
+    if (lead) {
+        for (int k = 0; k < kdev; k++) TRY(launch_round(k));
+        TRY(residual_enqueue(cur, 1 + nin, lres, kdev > 0, r, kdev > 0 ? d_chal + ((kdev - 1) & 1) : nullptr, W, &rtag));
+        if (!am_leader) return 0;
+        for (int k = 0; k < kdev; k++) TRY(transcript_round(k));
+    } else {
+        for (int k = 0; k < kdev; k++) {
+            TRY(launch_round(k));
+            TRY(transcript_round(k));
+        }
+        TRY(residual_enqueue(cur, 1 + nin, lres, kdev > 0, r, nullptr, W, &rtag));
     }
     // ---- residual tables (folded with the last device challenge) -> host, gathered over the ranks; host finishes
     H::Fr tabs[3][TAIL_MAX];
-    TRY(fetch_residual(cur, 1 + nin, (size_t)1 << tail_bits, kdev > 0, r, W, tabs));
-    host_tail(lagrange, tabs[0], tabs[1], tabs[2], ((size_t)1 << tail_bits) * (size_t)W, gate, ark, kdev, bn, proof_out, challenges_out, final_out, st);
+    TRY(residual_collect(1 + nin, lres, W, rtag, tabs));
+    host_tail(lagrange, tabs[0], tabs[1], tabs[2], lres * (size_t)W, gate, ark, kdev, bn, proof_out, challenges_out, final_out, st);
     return 0;
 }
 
@@ -998,16 +1170,13 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
     const int W = use_shards ? world : 1, LW = use_shards ? log_world : 0;
     const int bnl = bn - LW;
     if (bnl > 26) return fail(GKRB200_ERR_ARG, "too many variables (%d)", bnl);
+    const bool lead = lead_mode(W), am_leader = !lead || rank == leader;
     const H::Fr one = H::one();
     // this rank's slice of eq(q,.) carries the factor of its fixed low address bits
-    H::Fr seed_all[8];
-    for (int g = 0; g < W; g++) {
-        H::Fr sd = one;
-        for (int b = 0; b < LW; b++) {
-            const H::Fr& qb = q[bn - 1 - b];
-            sd = H::mul(sd, ((g >> b) & 1) ? qb : H::sub(one, qb));
-        }
-        seed_all[g] = sd;
+    H::Fr seed = one;
+    for (int b = 0; b < LW; b++) {
+        const H::Fr& qb = q[bn - 1 - b];
+        seed = H::mul(seed, ((rank >> b) & 1) ? qb : H::sub(one, qb));
     }
     const int c = bnl / 2;  // variables in the low suffix table
     int tail_bits = 0;  // the last rounds (residual table of at most tail_len entries over all ranks) are finished on the host
@@ -1016,7 +1185,7 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
     if (kdev > 0) {
         gkr::EqSuffixArgs ea{};
         memcpy(ea.q, q, (size_t)bnl * 32);
-        memcpy(&ea.seed, &seed_all[W > 1 ? rank : 0], 32);
+        memcpy(&ea.seed, &seed, 32);
         ea.n = bnl;
         ea.c = c;
         ea.outB = lo;
@@ -1031,14 +1200,19 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
     const FrRaw* cur[2] = {x0, x1};
     FrRaw* dstp[2] = {scratch[1], scratch[2]};
     H::Fr ck = one, cl = trusted_claim ? *trusted_claim : H::zero(), r = H::zero();
-    bool have_cl = trusted_claim != nullptr;
     H::Fr m[8], sc[8];
-    for (int k = 0; k < kdev; k++) {
+    uint32_t tags[32];
+    int nms[32];
+    bool par8s[32];
+    // round k runs on 7 sums when its claim is known (every round but an untrusted round 0) and q_k is invertible
+    auto launch_round = [&](int k) -> int {
         const int mk = bnl - 1 - k;  // variables of x'
         const size_t half = (size_t)1 << mk;
         const bool do_fold = k > 0;
-        const int nm = (have_cl && qinv_ok[k]) ? 7 : 8;
+        const int nm = ((k > 0 || trusted_claim != nullptr) && qinv_ok[k]) ? 7 : 8;
         const bool par8 = half <= par8_max_pairs;
+        nms[k] = nm;
+        par8s[k] = par8;
         gkr::RoundCfArgs a{};
         for (int i = 0; i < 2; i++) {
             a.src[i] = cur[i];
@@ -1046,6 +1220,7 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         }
         a.half = half;
         memcpy(&a.r, &r, 32);
+        a.r_dev = (lead && do_fold) ? d_chal + ((k - 1) & 1) : nullptr;
         memcpy(&a.ark, &ark, 32);
         if (mk > c) {
             a.tA = hi + ((size_t)1 << (mk - c));
@@ -1056,15 +1231,18 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         }
         a.c = c;
         const uint32_t tag = windowed(W) ? ++xseq : ++seq;
+        tags[k] = tag;
         a.red.partials = partials_w;
         a.red.ticket = ticket;
         a.red.result = windowed(W) ? (unsigned long long*)xslot_d(tag, rank) : (W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result);
         a.red.seq = tag;
+        a.red.chal = lead ? chal_wait(tag, k) : gkr::ChalWait{nullptr, nullptr, nullptr, 0};
         const int blk = par8 ? CF_BLOCK : CF_BLOCK1;
         int bps1 = cf_blocks_per_sm1[nm - 7];
         if (cf_blocks_cap > 0 && bps1 > cf_blocks_cap) bps1 = cf_blocks_cap;
         const int grid = grid_for(par8 ? half * 8 : half, blk, n_sm * (par8 ? CF_MINB8 : bps1));  // at most one resident wave
-        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, par8), grid, blk, cf_smem(nm, par8), a);
+        const int variant = par8 ? CF_V_PAR8 : (half >= inline_min_pairs ? CF_V_INL : CF_V_CALL);
+        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, variant), grid, blk, cf_smem(nm, par8), a);
         CUDA_TRY(cudaGetLastError());
         // algorithmic multiplier work in units of one Montgomery product (136 wide multiply-adds): 9 (NM = 8: 11) full products,
         // NM plain 512-bit products of 64 multiply-adds each, the eq factor product and four folds
@@ -1074,7 +1252,11 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
             cur[0] = dstp[0];
             cur[1] = dstp[1];
         }
-        TRY(exchange_and_fetch_wide(nm, par8 ? CF_WL8 : CF_WL1, W, tag, m));
+        return 0;
+    };
+    auto transcript_round = [&](int k) -> int {
+        const int nm = nms[k];
+        TRY(exchange_and_fetch_wide(nm, par8s[k] ? CF_WL8 : CF_WL1, W, tags[k], m));
         const double t0 = now_ms();
         const H::Fr w0 = H::sub(one, q[k]), w1 = H::sub(q[k], w0);  // eq(q_k, t) = w0 + w1*t
         if (nm == 7) {
@@ -1095,19 +1277,33 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         for (int j = 1; j < 8; j++) coeffs[j] = H::add(H::mul(cw0, sc[j]), H::mul(cw1, sc[j - 1]));
         coeffs[8] = H::mul(cw1, sc[7]);
         r = H::mimc_hash(coeffs, 9);  // common/challenge.go:10
+        if (lead) post_challenge(tags[k], r);
         challenges_out[k] = r;
         cl = H::eval_univariate(sc, 8, r);  // next round's claim / c_{k+1}
-        have_cl = true;
         ck = H::mul(ck, H::add(w0, H::mul(w1, r)));
         st.transcript_ms += now_ms() - t0;
         st.rounds++;
+        return 0;
+    };
+    uint32_t rtag = 0;
+    const size_t lres = (size_t)1 << tail_bits;
+    if (lead) {
+        for (int k = 0; k < kdev; k++) TRY(launch_round(k));
+        TRY(residual_enqueue(cur, 2, lres, kdev > 0, r, kdev > 0 ? d_chal + ((kdev - 1) & 1) : nullptr, W, &rtag));
+        if (!am_leader) return 0;
+        for (int k = 0; k < kdev; k++) TRY(transcript_round(k));
+    } else {
+        for (int k = 0; k < kdev; k++) {
+            TRY(launch_round(k));
+            TRY(transcript_round(k));
+        }
+        TRY(residual_enqueue(cur, 2, lres, kdev > 0, r, nullptr, W, &rtag));
     }
     // ---- residual X tables -> host (gathered over the ranks); the eq residual is closed-form: c_kdev * eq(q[kdev:], .)
     H::Fr tabs[3][TAIL_MAX];
-    TRY(fetch_residual(cur, 2, (size_t)1 << tail_bits, kdev > 0, r, W, tabs + 1));
+    TRY(residual_collect(2, lres, W, rtag, tabs + 1));
     host_eq_table(q + kdev, bn - kdev, ck, tabs[0]);
-    host_tail(lagrange, tabs[0], tabs[1], tabs[2], ((size_t)1 << tail_bits) * (size_t)W, gkr::GATE_CIPHER, ark, kdev, bn, proof_out, challenges_out,
-              final_out, st);
+    host_tail(lagrange, tabs[0], tabs[1], tabs[2], lres * (size_t)W, gkr::GATE_CIPHER, ark, kdev, bn, proof_out, challenges_out, final_out, st);
     return 0;
 }
 
@@ -1129,6 +1325,37 @@ static int pos_in_out(int producer, int consumer) { return producer == 2 ? consu
 static int n_coeffs(int layer) { return layer < 2 ? 0 : (layer == 2 ? 3 : 9); }
 
 extern "C" size_t gkrb200_proof_vec_len(int bn) { return (size_t)1006 * (size_t)bn + 183; }
+
+// The library proves ONE circuit, examples.MimcCircuit() (examples/mimc.go:10-37).  The Go shim hands over the description of
+// the circuit.Circuit it was called with and panics unless this returns 0 -- so gkr.Prove(c, a, qPrime) on any other circuit
+// fails loudly instead of silently proving the MiMC one.  Checks what BuildCircuit (circuit/circuit.go:28-44) and
+// IsInputLayer (:70-79) enforce as well: an input layer has no gate and no inputs and at most one consumer.
+extern "C" int gkrb200_check_mimc_circuit(int n_layers, const int* n_in, const int* in_flat, const int* gate_kinds, const uint64_t* arks) {
+    if (!n_in || !in_flat || !gate_kinds) return fail(GKRB200_ERR_ARG, "null circuit description");
+    if (n_layers != N_LAYERS) return fail(GKRB200_ERR_ARG, "circuit has %d layers, the MiMC circuit has %d", n_layers, N_LAYERS);
+    int consumers[N_LAYERS] = {0};
+    size_t cur = 0;
+    for (int l = 0; l < N_LAYERS; l++) {
+        int want[2];
+        const int k = layer_in(l, want);
+        if (n_in[l] != k) return fail(GKRB200_ERR_ARG, "layer %d has %d inputs, the MiMC circuit has %d", l, n_in[l], k);
+        for (int i = 0; i < k; i++) {
+            const int src = in_flat[cur + (size_t)i];
+            if (src != want[i]) return fail(GKRB200_ERR_ARG, "layer %d input %d is layer %d, the MiMC circuit wires layer %d", l, i, src, want[i]);
+            consumers[src]++;
+        }
+        cur += (size_t)k;
+        const int gate = k == 0 ? -1 : (l == 2 ? GKRB200_GATE_IDENTITY : GKRB200_GATE_CIPHER);
+        if (gate_kinds[l] != gate) return fail(GKRB200_ERR_ARG, "layer %d has gate kind %d, the MiMC circuit has %d (-1 = input layer)", l, gate_kinds[l], gate);
+        if (gate == GKRB200_GATE_CIPHER) {
+            if (!arks) return fail(GKRB200_ERR_ARG, "null round constants");
+            if (memcmp(arks + 4 * (size_t)l, &H::ARKS[l - 3], 32) != 0) return fail(GKRB200_ERR_ARG, "layer %d: the cipher gate's Ark is not hash.Arks[%d]", l, l - 3);
+        }
+    }
+    for (int l = 0; l < 2; l++)  // circuit/circuit.go:37-41: an input layer feeds at most one layer
+        if (consumers[l] > 1) return fail(GKRB200_ERR_ARG, "input layer %d has %d consumers", l, consumers[l]);
+    return 0;
+}
 
 extern "C" int gkrb200_gkr_prove_mimc(gkrb200_ctx* c, const uint64_t* qprime, int bn, uint64_t* proof_vec_out, uint32_t flags) {
     if (!c || !proof_vec_out || (bn > 0 && !qprime)) return fail(GKRB200_ERR_ARG, "null argument");
@@ -1153,15 +1380,30 @@ extern "C" int gkrb200_gkr_prove_mimc(gkrb200_ctx* c, const uint64_t* qprime, in
         const H::Fr ark = layer > 2 ? H::ARKS[layer - 3] : H::zero();
         const size_t n_q = layer == N_LAYERS - 1 ? 1 : (size_t)n_out(layer);
         const size_t n_cl = layer == N_LAYERS - 1 ? 0 : (size_t)n_out(layer);  // Claims[93] is nil (prover.go:27)
-        H::Fr fin[3];
+        H::Fr fin[4];
         // Claims[layer][0] was produced by this prover from the assignment it computed itself: it IS sum eq*gate of this layer
         const H::Fr* trusted = (gate == gkr::GATE_CIPHER && n_cl == 1) ? claims[layer].data() : nullptr;
         TRY(c->sumcheck(c->slot(in[0]), k > 1 ? c->slot(in[1]) : nullptr, bn, qps[layer].data(), n_q, claims[layer].data(), n_cl, gate, ark,
                         c->sharded, sc[layer].data(), challenges.data(), fin, trusted));
+        if (c->sharded && c->lead_mode(c->world)) {
+            // one transcript per proof: the leader posts this layer's round polynomials, challenges and final claims; the
+            // followers (which only enqueued their kernels) pick them up and stay in step
+            if (c->rank == c->leader) TRY(c->post_header(layer, sc[layer].data(), sc[layer].size(), challenges.data(), bn, fin, 1 + k));
+            else TRY(c->wait_header(layer, sc[layer].data(), sc[layer].size(), challenges.data(), bn, fin, 1 + k));
+        }
         for (int i = 0; i < k; i++) {  // prover.go:66-90
             const int at = pos_in_out(in[i], layer);
             claims[in[i]][(size_t)at] = fin[1 + i];
             if (bn) memcpy(&qps[in[i]][(size_t)at * ubn], challenges.data(), ubn * sizeof(H::Fr));
+        }
+    }
+    if (c->sharded && c->lead_mode(c->world)) {  // a round kernel that gave up waiting for its challenge leaves a mark
+        unsigned int derr = 0;
+        CUDA_TRY(cudaMemcpyAsync(&derr, c->d_err, sizeof derr, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (derr) {
+            cudaMemsetAsync(c->d_err, 0, sizeof derr, c->stream);
+            return fail(GKRB200_ERR_COMM, "a round kernel timed out waiting for the leader's challenge");
         }
     }
     // GkrProofToVec order (prover/gadget/hints.go:236-271)
@@ -1198,26 +1440,11 @@ extern "C" int gkrb200_convert(gkrb200_ctx* c, const uint64_t* in, size_t n, uin
 
 extern "C" int gkrb200_mimc_assign_ex(gkrb200_ctx* c, const uint64_t* key, const uint64_t* msg, size_t n, uint64_t* out, uint32_t flags) {
     int bn;
-    TRY(check_n(c, n, &bn));
+    TRY(check_n(c, n, &bn, true));
     if (!key || !msg) return fail(GKRB200_ERR_ARG, "null input table");
     if (flags & ~(GKRB200_IO_INPUT_REGULAR | GKRB200_IO_OUTPUT_REGULAR | GKRB200_IO_OUTPUT_HASH)) return fail(GKRB200_ERR_ARG, "unknown flags 0x%x", flags);
     CUDA_TRY(cudaSetDevice(c->device));
-    c->sharded = c->world > 1 && bn > c->log_world;
-    c->bn = bn;
-    if (!c->sharded) {
-        c->n_local = n;
-        TRY(c->upload(c->slot(0), key, n));
-        TRY(c->upload(c->slot(1), msg, n));
-    } else {
-        c->n_local = n / (size_t)c->world;
-        FrRaw* tmp_key = c->eq;
-        FrRaw* tmp_msg = c->scratch[0];
-        TRY(c->upload(tmp_key, key, n));
-        TRY(c->upload(tmp_msg, msg, n));
-        const int grid = grid_for(c->n_local, 256, c->n_sm * 8);
-        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_key, c->slot(0), c->n_local, c->world, c->rank);
-        LAUNCH(c, KC_STAGING, gkr::k_take_shard, grid, 256, 0, tmp_msg, c->slot(1), c->n_local, c->world, c->rank);
-    }
+    TRY(stage_inputs(c, key, msg, n, bn));
     if (flags & GKRB200_IO_INPUT_REGULAR) {  // SetBigInt of every input on the device (prover/gadget/hints.go:202-205)
         const int grid = grid_for(c->n_local, 256, c->n_sm * 8);
         LAUNCH(c, KC_STAGING, gkr::k_convert, grid, 256, 0, c->slot(0), c->slot(0), c->n_local, 1);
@@ -1385,35 +1612,53 @@ extern "C" int gkrb200_gkr_verify_mimc(gkrb200_ctx* c, const uint64_t* proof_vec
 }
 
 // ------------------------------------------------------------------------------------------------ sumcheck.Prove on host tables
-extern "C" int gkrb200_sumcheck_prove(gkrb200_ctx* c, const uint64_t* X0, const uint64_t* X1, int bn, const uint64_t* qprimes, size_t n_q,
-                                      const uint64_t* claims, size_t n_claims, int gate_kind, const uint64_t* ark, uint64_t* proof_out,
-                                      uint64_t* challenges_out, uint64_t* final_claims_out) {
+static int sumcheck_prove_common(gkrb200_ctx* c, const void* X0, const void* X1, bool on_device, int bn, const uint64_t* qprimes, size_t n_q,
+                                 const uint64_t* claims, size_t n_claims, int gate_kind, const uint64_t* ark, uint64_t* proof_out,
+                                 uint64_t* challenges_out, uint64_t* final_claims_out) {
     if (!c || !X0 || bn < 0 || n_q < 1 || (bn > 0 && !qprimes) || !final_claims_out) return fail(GKRB200_ERR_ARG, "bad argument");
     if (gate_kind != GKRB200_GATE_IDENTITY && gate_kind != GKRB200_GATE_CIPHER)
         return fail(GKRB200_ERR_ARG, "gate kind %d cannot cross the ABI (only IdentityGate and CipherGate)", gate_kind);
     if (gate_kind == GKRB200_GATE_CIPHER && !X1) return fail(GKRB200_ERR_ARG, "cipher gate needs two input tables");
-    if (bn > c->max_bn) return fail(GKRB200_ERR_OOM, "table 2^%d exceeds the context capacity 2^%d", bn, c->max_bn);
+    if (bn > c->cap_bn) return fail(GKRB200_ERR_OOM, "table 2^%d exceeds the context capacity 2^%d", bn, c->cap_bn);
     if (n_claims && !claims) return fail(GKRB200_ERR_ARG, "null claims");
     CUDA_TRY(cudaSetDevice(c->device));
     const size_t n = (size_t)1 << bn;
+    const FrRaw *d0 = (const FrRaw*)X0, *d1 = (const FrRaw*)X1;
     FrRaw* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, 2 * n * sizeof(FrRaw)));
-    int rc = c->upload(d, X0, n);
-    if (!rc && gate_kind == GKRB200_GATE_CIPHER) rc = c->upload(d + n, X1, n);
+    int rc = 0;
+    if (!on_device) {
+        CUDA_TRY(cudaMalloc(&d, 2 * n * sizeof(FrRaw)));
+        rc = c->upload(d, X0, n);
+        if (!rc && gate_kind == GKRB200_GATE_CIPHER) rc = c->upload(d + n, X1, n);
+        d0 = d;
+        d1 = d + n;
+    }
     H::Fr a = H::zero();
     if (ark) memcpy(&a, ark, 32);
     if (!rc)
-        rc = c->sumcheck(d, gate_kind == GKRB200_GATE_CIPHER ? d + n : nullptr, bn, (const H::Fr*)qprimes, n_q, (const H::Fr*)claims, n_claims,
+        rc = c->sumcheck(d0, gate_kind == GKRB200_GATE_CIPHER ? d1 : nullptr, bn, (const H::Fr*)qprimes, n_q, (const H::Fr*)claims, n_claims,
                          gate_kind, a, false, (H::Fr*)proof_out, (H::Fr*)challenges_out, (H::Fr*)final_claims_out);
-    cudaStreamSynchronize(c->stream);
-    cudaFree(d);
+    if (d) {
+        cudaStreamSynchronize(c->stream);
+        cudaFree(d);
+    }
     return rc;
+}
+extern "C" int gkrb200_sumcheck_prove(gkrb200_ctx* c, const uint64_t* X0, const uint64_t* X1, int bn, const uint64_t* qprimes, size_t n_q,
+                                      const uint64_t* claims, size_t n_claims, int gate_kind, const uint64_t* ark, uint64_t* proof_out,
+                                      uint64_t* challenges_out, uint64_t* final_claims_out) {
+    return sumcheck_prove_common(c, X0, X1, false, bn, qprimes, n_q, claims, n_claims, gate_kind, ark, proof_out, challenges_out, final_claims_out);
+}
+extern "C" int gkrb200_sumcheck_prove_device(gkrb200_ctx* c, const void* d_X0, const void* d_X1, int bn, const uint64_t* qprimes, size_t n_q,
+                                             const uint64_t* claims, size_t n_claims, int gate_kind, const uint64_t* ark, uint64_t* proof_out,
+                                             uint64_t* challenges_out, uint64_t* final_claims_out) {
+    return sumcheck_prove_common(c, d_X0, d_X1, true, bn, qprimes, n_q, claims, n_claims, gate_kind, ark, proof_out, challenges_out, final_claims_out);
 }
 
 // ------------------------------------------------------------------------------------------------ building blocks
 extern "C" int gkrb200_eq_table(gkrb200_ctx* c, const uint64_t* qprimes, size_t n_q, int bn, const uint64_t* multipliers, uint64_t* out) {
     if (!c || !out || bn < 0 || (bn > 0 && !qprimes)) return fail(GKRB200_ERR_ARG, "bad argument");
-    if (bn > c->max_bn) return fail(GKRB200_ERR_OOM, "table 2^%d exceeds the context capacity 2^%d", bn, c->max_bn);
+    if (bn > c->cap_bn) return fail(GKRB200_ERR_OOM, "table 2^%d exceeds the context capacity 2^%d", bn, c->cap_bn);
     CUDA_TRY(cudaSetDevice(c->device));
     TRY(c->build_eq((const H::Fr*)qprimes, n_q, bn, (const H::Fr*)multipliers, c->eq));
     CUDA_TRY(cudaMemcpyAsync(out, c->eq, ((size_t)1 << bn) * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream));
@@ -1468,16 +1713,16 @@ extern "C" int gkrb200_round_eval(gkrb200_ctx* c, const uint64_t* eq, const uint
         ++c->seq;
         a.red.partials = c->partials;
         a.red.ticket = c->ticket;
-        a.red.result = c->h_result;
-        a.red.flag = c->h_flag;
+        a.red.result = (unsigned long long*)c->h_result;
         a.red.seq = c->seq;
         const int nev = gate_kind == GKRB200_GATE_CIPHER ? 9 : 3;
         const int grid = grid_for(a.half, ROUND_BLOCK, c->max_grid);
         const size_t smem = (size_t)nev * 9 * ROUND_BLOCK * 4;
         auto kf = gate_kind == GKRB200_GATE_CIPHER ? gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK, ROUND_MINB> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>;
         LAUNCH(c, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
-        rc = c->wait_flag(c->seq);
-        if (!rc) memcpy(evals_out, (const void*)c->h_result, (size_t)nev * 32);
+        H::Fr ev[MAX_EV];
+        rc = c->exchange_and_fetch_wide(nev, 9, 1, c->seq, ev);
+        if (!rc) memcpy(evals_out, ev, (size_t)nev * 32);
     }
     cudaStreamSynchronize(c->stream);
     cudaFree(d);
@@ -1636,6 +1881,14 @@ extern "C" int gkrb200_set_option(gkrb200_ctx* c, int option, long value) {
             if (value < 0 || value > 32) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
             c->cf_blocks_cap = (int)value;
             return 0;
+        case GKRB200_OPT_INLINE_MIN_PAIRS:
+            if (value < 0) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
+            c->inline_min_pairs = (size_t)value;
+            return 0;
+        case GKRB200_OPT_TRANSCRIPT:
+            if (value != 0 && value != 1) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
+            c->replicated_transcript = value == 1;
+            return 0;
         case GKRB200_OPT_EXCHANGE:
             if (value != 0 && value != 1) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
             if (value == 0 && c->world > 1 && !c->x_base) return fail(GKRB200_ERR_STATE, "this communicator has no exchange window");
@@ -1654,7 +1907,7 @@ extern "C" int gkrb200_trace_get(long long* out16) {
 extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, double* rate_out, double* ms_out) {
     // low byte: kind; next byte (optional): warps per SM to allow (occupancy limited through dynamic shared memory)
     const int kind = kind_and_occ & 0xff, warps = (kind_and_occ >> 8) & 0xff;
-    if (!c || !rate_out || iters < 1 || kind < 0 || kind > 5) return fail(GKRB200_ERR_ARG, "bad argument");  // 4 / 5: kind 1 with the schoolbook / Karatsuba multiplier
+    if (!c || !rate_out || iters < 1 || kind < 0 || kind > 4) return fail(GKRB200_ERR_ARG, "bad argument");  // 4: kind 1 through the out-of-line multiplier (call ABI cost)
     CUDA_TRY(cudaSetDevice(c->device));
     int block = 256, grid = c->n_sm * 8;
     size_t smem = 0;
@@ -1666,7 +1919,6 @@ extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, d
         grid = c->n_sm * blocks_per_sm * 2;
         CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(gkr::k_bench_fr_mul1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     void* d = nullptr;
@@ -1680,7 +1932,6 @@ extern "C" int gkrb200_microbench(gkrb200_ctx* c, int kind_and_occ, int iters, d
         if (kind == 0) gkr::k_bench_imad_wide<<<grid, block, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
         else if (kind == 1) gkr::k_bench_fr_mul<0><<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
         else if (kind == 4) gkr::k_bench_fr_mul<1><<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
-        else if (kind == 5) gkr::k_bench_fr_mul<2><<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
         else if (kind == 2) gkr::k_bench_imad_wide_x<<<grid, block, 0, c->stream>>>((uint64_t*)d, iters, 12345u + rep);
         else gkr::k_bench_fr_mul1<<<grid, block, smem, c->stream>>>((FrRaw*)d, iters, 12345u + rep);
         cudaEventRecord(e1, c->stream);

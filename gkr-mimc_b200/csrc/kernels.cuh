@@ -55,54 +55,63 @@ __device__ __forceinline__ void smem_tree_reduce(uint32_t* sm, int tid) {
     }
 }
 
-struct ReduceOut {
-    FrRaw* partials;         // [gridDim.x][NACC] device scratch
-    unsigned int* ticket;    // device counter, zero between launches
-    FrRaw* result;           // NACC elements; device memory or mapped pinned host memory
-    volatile uint32_t* flag; // optional: set to seq (after a system fence) once result is written
-    uint32_t seq;
-};
-
-// Every thread contributes acc[NACC]; the grid total lands in out.result (written by one thread of the last block).
-template <int NACC, int BLOCK>
-__device__ __forceinline__ void grid_reduce(const Fr (&acc)[NACC], const ReduceOut& out, uint32_t* sm) {
-    const int tid = threadIdx.x;
-#pragma unroll
-    for (int k = 0; k < NACC; k++) smem_put<NACC, BLOCK>(sm, k, tid, acc[k]);
-    smem_tree_reduce<NACC, BLOCK>(sm, tid);
-    __shared__ bool is_last;
-    if (gridDim.x == 1) {
-        if (tid < NACC) fr_store(out.result + tid, smem_get<BLOCK>(sm, tid, 0));
-    } else {
-        if (tid < NACC) fr_store(out.partials + (size_t)blockIdx.x * NACC + tid, smem_get<BLOCK>(sm, tid, 0));
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) is_last = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        // last block: sum the per-block partials
-#pragma unroll 1
-        for (int k = 0; k < NACC; k++) {
-            Fr s = fr_zero();
-#pragma unroll 1
-            for (unsigned b = tid; b < gridDim.x; b += BLOCK) s = fr_add(s, fr_load(out.partials + (size_t)b * NACC + k));
-#pragma unroll
-            for (int l = 0; l < 8; l++) sm[(k * 8 + l) * BLOCK + tid] = s.v[l];
-        }
-        smem_tree_reduce<NACC, BLOCK>(sm, tid);
-        if (tid < NACC) fr_store(out.result + tid, smem_get<BLOCK>(sm, tid, 0));
-        if (tid == 0) *out.ticket = 0;
-    }
-    if (out.flag) {
-        if (tid < NACC) __threadfence_system();  // publish this thread's result element before the barrier
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            *out.flag = out.seq;
-        }
-    }
+// ------------------------------------------------------------------------------------------------
+// Publishing results and receiving the verifier challenge.
+//
+// Publishing without fences: every 64-bit word carries the launch tag in its upper half and is written with one aligned
+// 8-byte store, so the consumer (a host thread spinning on mapped pinned memory, or a later kernel) needs no flag and no
+// ordering between words -- it waits until all words show the tag.  Saves the two system-scope fences (~3 us measured) a
+// flag protocol costs per round.  The challenge r_k = MimcHash(round polynomial) comes back the same way: the host that
+// owns the proof's transcript writes 8 tagged words into mapped memory and the LAST block of the round kernel (all other
+// blocks have exited, the SMs are free for other streams) polls them and stores r_k to device memory, where the next
+// launch on the stream -- already enqueued -- reads it.  No host thread of this GPU takes part in a round.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void publish_word(unsigned long long* dst, uint32_t seq, uint32_t limb) {
+    const unsigned long long v = ((unsigned long long)seq << 32) | limb;
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long poll_word(const unsigned long long* src) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+struct ChalWait {
+    const unsigned long long* src;  // 8 tagged words (mapped host memory, device alias); nullptr: the kernel does not wait
+    FrRaw* dst;                     // device memory that receives the challenge (read by the next launch on the stream)
+    unsigned int* err;              // device flag: set to 1 when the challenge did not arrive within CHAL_TIMEOUT_NS
+    uint32_t tag;
+};
+constexpr unsigned long long CHAL_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;  // never hang the box: give up after 20 s
+// called by every thread of the one block that published; lanes 0..7 each fetch one limb
+__device__ __forceinline__ void wait_challenge(const ChalWait& w) {
+    if (!w.src || threadIdx.x >= 8) return;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned long long v = poll_word(w.src + threadIdx.x);
+    while ((uint32_t)(v >> 32) != w.tag) {
+        __nanosleep(200);
+        v = poll_word(w.src + threadIdx.x);
+        if (global_timer_ns() - t0 > CHAL_TIMEOUT_NS) {
+            atomicExch(w.err, 1u);
+            break;
+        }
+    }
+    reinterpret_cast<uint32_t*>(w.dst)[threadIdx.x] = (uint32_t)v;
+}
+
+// Output of the generic round kernel: NEV canonical field elements, each as 9 tagged words (8 limbs + a zero word: the same
+// 288-bit image the factored kernel's reduced sums use, so one host routine reads both).
+struct ReduceOut {
+    FrRaw* partials;             // [gridDim.x][NEV] device scratch
+    unsigned int* ticket;        // device counter, zero between launches
+    unsigned long long* result;  // NEV x 9 tagged words; device memory or mapped host memory
+    uint32_t seq;
+    ChalWait chal;
+};
 
 // ------------------------------------------------------------------------------------------------
 // K1: batched MiMC layer assignment.  One thread = one hash; the 91 round states go to layers 3..93.
@@ -153,7 +162,7 @@ __global__ void __launch_bounds__(256) k_eq_small(const FrRaw* __restrict__ qpri
 // K2/K5 stage 2: out[x] = sum_j hi_j[x >> nl] * lo_j[x & (2^nl-1)]   (one streaming write of the table)
 // The 91 products of an entry only feed a sum, so they are taken as PLAIN 512-bit products (64 instead of 136 wide
 // multiply-adds each, fr_mul_acc_wide on a 17-limb accumulator in shared memory) and reduced in groups of five: 5*q^2 <
-// q*2^256 is exactly the input range of one Montgomery reduction (hd_redc), and REDC(sum of products) is the sum of the
+// q*2^256 is exactly the input range of one Montgomery reduction (fr_redc_wide), and REDC(sum of products) is the sum of the
 // Montgomery products, so the result is the same canonical element.  91 claims: 7 192 instead of 12 376 wide multiply-adds.
 constexpr int EQX_BLOCK = 256, EQX_GROUP = 5;
 __global__ void __launch_bounds__(EQX_BLOCK) k_eq_expand(const FrRaw* __restrict__ hi, const FrRaw* __restrict__ lo, int nh, int nl, int n_claims,
@@ -177,7 +186,7 @@ __global__ void __launch_bounds__(EQX_BLOCK) k_eq_expand(const FrRaw* __restrict
             uint32_t t[16];
 #pragma unroll
             for (int l = 0; l < 16; l++) t[l] = acc[l * EQX_BLOCK + tid];  // limb 16 stays zero: 5*q^2 < 2^512
-            total = fr_add(total, hd_redc(t));
+            total = fr_add(total, fr_redc_wide(t));
         }
         fr_store(out + x, total);
     }
@@ -192,9 +201,10 @@ struct FoldArgs {
     int n_tables;
     size_t half;
     FrRaw r;
+    const FrRaw* r_dev;  // when not null: the challenge is read from device memory instead of a.r
 };
 __global__ void __launch_bounds__(256) k_fold(const FoldArgs a) {
-    const Fr r = fr_unpack(a.r);
+    const Fr r = a.r_dev ? fr_load(a.r_dev) : fr_unpack(a.r);
     const size_t total = a.half * (size_t)a.n_tables;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int t = (int)(i / a.half);
@@ -216,8 +226,9 @@ struct RoundArgs {
     const FrRaw* src[3];  // eq, X0, X1
     FrRaw* dst[3];
     size_t half;
-    FrRaw r;    // previous challenge (FOLD)
-    FrRaw ark;  // cipher gate constant
+    FrRaw r;             // previous challenge (FOLD) ...
+    const FrRaw* r_dev;  // ... or, when not null, where a previous launch left it in device memory
+    FrRaw ark;           // cipher gate constant
     ReduceOut red;
 };
 
@@ -333,9 +344,7 @@ __device__ __forceinline__ void grid_reduce_wide(uint32_t* sm, const ReduceOut& 
         for (int l = 0; l < 9; l++) w[l] = sm[(tid * 9 + l) * BLOCK];
         mine = fr_from_wide(w);
     }
-    if (gridDim.x == 1) {
-        if (tid < NEV) fr_store(out.result + tid, mine);
-    } else {
+    if (gridDim.x > 1) {
         if (tid < NEV) fr_store(out.partials + (size_t)blockIdx.x * NEV + tid, mine);
         __threadfence();
         __syncthreads();
@@ -353,17 +362,15 @@ __device__ __forceinline__ void grid_reduce_wide(uint32_t* sm, const ReduceOut& 
             for (int l = 0; l < 8; l++) sm[(k * 8 + l) * BLOCK + tid] = s.v[l];
         }
         smem_tree_reduce<NEV, BLOCK>(sm, tid);
-        if (tid < NEV) fr_store(out.result + tid, smem_get<BLOCK>(sm, tid, 0));
+        if (tid < NEV) mine = smem_get<BLOCK>(sm, tid, 0);
         if (tid == 0) *out.ticket = 0;
     }
-    if (out.flag) {
-        if (tid < NEV) __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence_system();
-            *out.flag = out.seq;
-        }
+    if (tid < NEV) {
+#pragma unroll
+        for (int l = 0; l < 8; l++) publish_word(out.result + tid * 9 + l, out.seq, mine.v[l]);
+        publish_word(out.result + tid * 9 + 8, out.seq, 0u);
     }
+    wait_challenge(out.chal);
 }
 
 template <int GATE, bool FOLD, int BLOCK, int MINB>
@@ -373,7 +380,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round(const RoundArgs a) {
     const int tid = threadIdx.x;
 #pragma unroll 1
     for (int i = tid; i < NEV * 9 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
-    const Fr r = fr_unpack(a.r);
+    const Fr r = a.r_dev ? fr_load(a.r_dev) : fr_unpack(a.r);
 
     for (size_t x = (size_t)blockIdx.x * BLOCK + tid; x < a.half; x += (size_t)gridDim.x * BLOCK) {
         Fr e, de, s, ds;
@@ -438,6 +445,14 @@ __device__ long long g_trace[16];
 #define GKR_T(i) do { } while (0)
 #endif
 
+// a += b as WL-limb integers (WL = 9 or 17); every carry chain is one asm statement, carries cross statements in a register
+template <int WL>
+__device__ __forceinline__ void widen_add(uint32_t (&a)[WL], const uint32_t (&b)[WL]) {
+    static_assert(WL == 9 || WL == 17, "288- or 544-bit accumulators");
+    uint32_t c = add8_carry(a, b);
+    if (WL == 17) c = add8_carry_in(a + 8, b + 8, c);
+    a[WL - 1] += b[WL - 1] + c;
+}
 // sm[(k*WL + l)*BLOCK + i] += sm[(k*WL + l)*BLOCK + i + stride]  as WL-limb integers
 template <int WL, int BLOCK>
 __device__ __forceinline__ void widen_pair_add(uint32_t* sm, int k, int i, int stride) {
@@ -447,19 +462,9 @@ __device__ __forceinline__ void widen_pair_add(uint32_t* sm, int k, int i, int s
         a[l] = sm[(k * WL + l) * BLOCK + i];
         b[l] = sm[(k * WL + l) * BLOCK + i + stride];
     }
-    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a[0]) : "r"(b[0]));
-#pragma unroll
-    for (int l = 1; l < WL - 1; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(a[l]) : "r"(b[l]));
-    asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[WL - 1]) : "r"(b[WL - 1]));
+    widen_add<WL>(a, b);
 #pragma unroll
     for (int l = 0; l < WL; l++) sm[(k * WL + l) * BLOCK + i] = a[l];
-}
-template <int WL>
-__device__ __forceinline__ void widen_add(uint32_t (&a)[WL], const uint32_t (&b)[WL]) {
-    asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(a[0]) : "r"(b[0]));
-#pragma unroll
-    for (int l = 1; l < WL - 1; l++) asm volatile("addc.cc.u32 %0, %0, %1;" : "+r"(a[l]) : "r"(b[l]));
-    asm volatile("addc.u32 %0, %0, %1;" : "+r"(a[WL - 1]) : "r"(b[WL - 1]));
 }
 
 struct WideOut {
@@ -468,6 +473,7 @@ struct WideOut {
     unsigned long long* result;    // NM x 9 words, each (seq << 32) | limb of a 288-bit plain sum (NOT reduced mod q);
                                    // device memory or mapped host memory
     uint32_t seq;                  // tag of this launch: the consumer polls until every word carries it
+    ChalWait chal;                 // optional: the block that publishes then waits for the challenge derived from the sums
 };
 
 // a += b as 288-bit integers (9 x 32-bit limbs)
@@ -485,15 +491,6 @@ __device__ __forceinline__ void wide9_add(uint32_t (&a)[9], const uint32_t (&b)[
         : "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]));
 }
 
-// Publishing without fences: every 64-bit word carries the launch tag in its upper half and is written with one
-// aligned 8-byte store, so the consumer (host spinning on mapped pinned memory, or a later kernel) needs no flag
-// and no ordering between words -- it waits until all NM*9 words show the tag.  Saves the two system-scope fences
-// (~3 us measured) a flag protocol costs per round.
-__device__ __forceinline__ void publish_word(unsigned long long* dst, uint32_t seq, uint32_t limb) {
-    const unsigned long long v = ((unsigned long long)seq << 32) | limb;
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(dst), "l"(v) : "memory");
-}
-
 // Grid stage shared by both layouts of k_round_cf.  tot: this block's NM x 9 limb sums in shared memory
 // (tot[k*WL + l]); scratch: >= 2 * NM * WL words of shared memory.  No field multiplication anywhere:
 // the host reduces the NM wide sums modulo q.
@@ -505,6 +502,7 @@ __device__ __forceinline__ void grid_stage_wide(const uint32_t* tot, uint32_t* s
     if (gridDim.x == 1) {
         for (int i = tid; i < NM * WL; i += BLOCK) publish_word(out.result + i, out.seq, tot[i]);
         GKR_T(6);
+        wait_challenge(out.chal);
         return;
     }
     // Every block adds its NM x WL limbs to 64-bit COLUMN sums in global memory (RED.ADD.64, fire and forget: a column
@@ -537,6 +535,7 @@ __device__ __forceinline__ void grid_stage_wide(const uint32_t* tot, uint32_t* s
     }
     if (tid == 0) *out.ticket = 0;
     GKR_T(6);
+    wait_challenge(out.chal);
 }
 
 // PAR = 1 layout: per-thread WL-limb accumulators in shared memory (sm[(k*WL+l)*BLOCK + tid]) -> block tree -> grid stage
@@ -607,7 +606,8 @@ struct RoundCfArgs {
     const FrRaw* src[2];  // X0, X1 (FOLD: length 4*half, else 2*half)
     FrRaw* dst[2];        // FOLD: folded tables, length 2*half
     size_t half;          // number of pairs x'
-    FrRaw r;              // previous challenge (FOLD)
+    FrRaw r;              // previous challenge (FOLD) ...
+    const FrRaw* r_dev;   // ... or, when not null, where the previous launch's last block left it in device memory
     FrRaw ark;            // CipherGate.Ark
     const FrRaw* tA;      // high suffix table of this round or nullptr
     const FrRaw* tB;      // low table (2^c entries when tA != nullptr, else `half` entries)
@@ -626,7 +626,20 @@ __device__ __forceinline__ Fr load_fold_one(const FrRaw* src, FrRaw* dst, size_t
     return fr_load_stream(src + idx);
 }
 
-template <bool FOLD, int NM, int PAR, int BLOCK, int MINB>
+// INL: the multiplier is inlined at every call site (big rounds: no call ABI, no IMAD.MOV marshalling on the multiplier's
+// pipe) or called out of line (small rounds: short cold instruction fetch)
+template <bool INL>
+__device__ __forceinline__ Fr cf_mul(const Fr& a, const Fr& b) {
+    if (INL) return fr_mul(a, b);
+    return fr_mulc(a, b);
+}
+template <bool INL>
+__device__ __forceinline__ void cf_acc(uint32_t* acc, int stride, const Fr& a, const Fr& b) {
+    if (INL) fr_mul_acc_wide_inl(acc, stride, a, b);
+    else fr_mul_acc_wide(acc, stride, a, b);
+}
+
+template <bool FOLD, int NM, int PAR, int BLOCK, int MINB, bool INL>
 __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
     static_assert(NM == 7 || NM == 8, "7 coefficient sums (m_7 from the claim) or all 8");
     static_assert(PAR == 1 || PAR == 8, "one thread or eight lanes per pair");
@@ -639,7 +652,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
         for (int i = tid; i < NM * WL1 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
     }
     GKR_T(1);
-    const Fr r = fr_unpack(a.r);
+    const Fr r = (FOLD && a.r_dev) ? fr_load(a.r_dev) : fr_unpack(a.r);
     const Fr ark = fr_unpack(a.ark);
     const size_t half = a.half, m2 = 2 * half;
     const size_t cmask = ((size_t)1 << a.c) - 1;
@@ -660,13 +673,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
                 const Fr l1 = fr_load_stream(a.src[0] + x + half), h1 = fr_load_stream(a.src[0] + x + half + m2);
                 const Fr l2 = fr_load_stream(a.src[1] + x), h2 = fr_load_stream(a.src[1] + x + m2);
                 const Fr l3 = fr_load_stream(a.src[1] + x + half), h3 = fr_load_stream(a.src[1] + x + half + m2);
-                const Fr b0 = fr_add(l0, fr_mulc(r, fr_sub(h0, l0)));
+                const Fr b0 = fr_add(l0, cf_mul<INL>(r, fr_sub(h0, l0)));
                 fr_store(a.dst[0] + x, b0);
-                const Fr t0 = fr_add(l1, fr_mulc(r, fr_sub(h1, l1)));
+                const Fr t0 = fr_add(l1, cf_mul<INL>(r, fr_sub(h1, l1)));
                 fr_store(a.dst[0] + x + half, t0);
-                const Fr b1 = fr_add(l2, fr_mulc(r, fr_sub(h2, l2)));
+                const Fr b1 = fr_add(l2, cf_mul<INL>(r, fr_sub(h2, l2)));
                 fr_store(a.dst[1] + x, b1);
-                const Fr t1 = fr_add(l3, fr_mulc(r, fr_sub(h3, l3)));
+                const Fr t1 = fr_add(l3, cf_mul<INL>(r, fr_sub(h3, l3)));
                 fr_store(a.dst[1] + x + half, t1);
                 av = fr_add(fr_add(b0, b1), ark);                 // cipher.go:34-35 on the bottom half
                 bv = fr_add(fr_sub(t0, b0), fr_sub(t1, b1));      // (top + ark) - (bottom + ark)
@@ -676,34 +689,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
                 av = fr_add(fr_add(b0, b1), ark);
                 bv = fr_add(fr_sub(t0, b0), fr_sub(t1, b1));
             }
-            Fr u = a.tA ? fr_mulc(ua, ub) : ub;
+            Fr u = a.tA ? cf_mul<INL>(ua, ub) : ub;
             // m_i = T a^(7-i) b^i as (T * degree-4 monomial) * (degree-3 monomial): the four cubic monomials (6 products),
             // T a, T a^4 and T a b^3 (3 products) give all of m_0..m_6 as products that only feed the sums, and those are
             // accumulated UNREDUCED (fr_mul_acc_wide).  9 Montgomery products per pair instead of 11 for powers + chain.
             Fr v30, v21, v12, v03;
             {
-                const Fr a2 = fr_sqrc(av), b2 = fr_sqrc(bv);
-                v30 = fr_mulc(a2, av);
-                v21 = fr_mulc(a2, bv);
-                v12 = fr_mulc(av, b2);
-                v03 = fr_mulc(b2, bv);
+                const Fr a2 = cf_mul<INL>(av, av), b2 = cf_mul<INL>(bv, bv);
+                v30 = cf_mul<INL>(a2, av);
+                v21 = cf_mul<INL>(a2, bv);
+                v12 = cf_mul<INL>(av, b2);
+                v03 = cf_mul<INL>(b2, bv);
             }
             if (NM == 8) {  // m_7 = (T b * b^3) * b^3
-                const Fr tb4 = fr_mulc(fr_mulc(u, bv), v03);
-                fr_mul_acc_wide(sm + (size_t)7 * WL1 * BLOCK + tid, BLOCK, tb4, v03);
+                const Fr tb4 = cf_mul<INL>(cf_mul<INL>(u, bv), v03);
+                cf_acc<INL>(sm + (size_t)7 * WL1 * BLOCK + tid, BLOCK, tb4, v03);
             }
-            u = fr_mulc(u, av);  // T a
+            u = cf_mul<INL>(u, av);  // T a
             {
-                const Fr u1 = fr_mulc(u, v03);  // T a b^3
-                fr_mul_acc_wide(sm + (size_t)4 * WL1 * BLOCK + tid, BLOCK, u1, v21);
-                fr_mul_acc_wide(sm + (size_t)5 * WL1 * BLOCK + tid, BLOCK, u1, v12);
-                fr_mul_acc_wide(sm + (size_t)6 * WL1 * BLOCK + tid, BLOCK, u1, v03);
+                const Fr u1 = cf_mul<INL>(u, v03);  // T a b^3
+                cf_acc<INL>(sm + (size_t)4 * WL1 * BLOCK + tid, BLOCK, u1, v21);
+                cf_acc<INL>(sm + (size_t)5 * WL1 * BLOCK + tid, BLOCK, u1, v12);
+                cf_acc<INL>(sm + (size_t)6 * WL1 * BLOCK + tid, BLOCK, u1, v03);
             }
-            u = fr_mulc(u, v30);  // T a^4
-            fr_mul_acc_wide(sm + (size_t)3 * WL1 * BLOCK + tid, BLOCK, u, v03);
-            fr_mul_acc_wide(sm + (size_t)2 * WL1 * BLOCK + tid, BLOCK, u, v12);
-            fr_mul_acc_wide(sm + (size_t)1 * WL1 * BLOCK + tid, BLOCK, u, v21);
-            fr_mul_acc_wide(sm + tid, BLOCK, u, v30);
+            u = cf_mul<INL>(u, v30);  // T a^4
+            cf_acc<INL>(sm + (size_t)3 * WL1 * BLOCK + tid, BLOCK, u, v03);
+            cf_acc<INL>(sm + (size_t)2 * WL1 * BLOCK + tid, BLOCK, u, v12);
+            cf_acc<INL>(sm + (size_t)1 * WL1 * BLOCK + tid, BLOCK, u, v21);
+            cf_acc<INL>(sm + tid, BLOCK, u, v30);
         }
     } else {
         const int j = tid & 7;
@@ -818,26 +831,19 @@ __global__ void k_publish_tagged(const uint32_t* __restrict__ src, int n, unsign
 // ------------------------------------------------------------------------------------------------
 // Multi-GPU helpers
 // ------------------------------------------------------------------------------------------------
+// de-interleave a contiguous slice by owner rank: dst[d*(n/G) + j] = src[j*G + d]  (block d is what rank d receives)
+__global__ void __launch_bounds__(256) k_destripe(const FrRaw* __restrict__ src, FrRaw* __restrict__ dst, size_t n, int G) {
+    const size_t blk = n / (size_t)G;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (size_t)gridDim.x * blockDim.x) {
+        const size_t d = o / blk, j = o - d * blk;
+        fr_store(dst + o, fr_load_stream(src + j * (size_t)G + d));
+    }
+}
 // strided shard of a full table: dst[j] = src[j*G + g]
 __global__ void __launch_bounds__(256) k_take_shard(const FrRaw* __restrict__ src, FrRaw* __restrict__ dst, size_t n_local, int G, int g) {
     for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_local; j += (size_t)gridDim.x * blockDim.x)
         fr_store(dst + j, fr_load_stream(src + j * (size_t)G + g));
 }
-// result[k] = sum_g all[g*nacc + k]; then raise the flag
-__global__ void k_sum_ranks(const FrRaw* __restrict__ all, int G, int nacc, FrRaw* result, volatile uint32_t* flag, uint32_t seq) {
-    const int k = threadIdx.x;
-    if (k < nacc) {
-        Fr s = fr_load(all + k);
-        for (int g = 1; g < G; g++) s = fr_add(s, fr_load(all + (size_t)g * nacc + k));
-        fr_store(result + k, s);
-    }
-    __syncthreads();
-    if (k == 0 && flag) {
-        __threadfence_system();
-        *flag = seq;
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Hint I/O (prover/gadget/hints.go:197-233): batched Montgomery <-> regular conversion and the user-visible hash
 // ------------------------------------------------------------------------------------------------
@@ -912,9 +918,9 @@ __global__ void __launch_bounds__(256) k_bench_imad_wide(uint64_t* out, int iter
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
 }
 // kind 1: two independent dependent-chains of fr_mul per thread (what the prover kernels look like)
-template <int MULT>  // 0: the library's multiplier (fr_mul), 1: schoolbook form, 2: Karatsuba form
+template <int MULT>  // 0: the library's multiplier (fr_mul), 1: the out-of-line copy (fr_mulc)
 __device__ __forceinline__ Fr bench_mul(const Fr& a, const Fr& b) {
-    return MULT == 1 ? fr_mul_school(a, b) : (MULT == 2 ? hd_mul_k(a, b) : fr_mul(a, b));
+    return MULT == 1 ? fr_mulc(a, b) : fr_mul(a, b);
 }
 template <int MULT>
 __global__ void k_bench_fr_mul(FrRaw* out, int iters, uint32_t seed) {

@@ -24,6 +24,7 @@ class Stats(ctypes.Structure):
         ("bytes_round", ctypes.c_uint64),
         ("h2d_bytes", ctypes.c_uint64),
         ("d2h_bytes", ctypes.c_uint64),
+        ("follow_wait_ms", ctypes.c_double),
     ]
 
 
@@ -53,6 +54,7 @@ def lib():
     L.gkrb200_free.restype = None
     L.gkrb200_comm_unique_id.argtypes = [vp]
     L.gkrb200_comm_init.argtypes = [vp, i32, i32, vp]
+    L.gkrb200_comm_set_leader.argtypes = [vp, i32]
     L.gkrb200_comm_exchange_mode.argtypes = [vp]
     L.gkrb200_mimc_assign.argtypes = [vp, vp, vp, sz, vp]
     L.gkrb200_mimc_assign_device.argtypes = [vp, vp, vp, sz]
@@ -61,6 +63,8 @@ def lib():
     L.gkrb200_proof_vec_len.argtypes = [i32]
     L.gkrb200_proof_vec_len.restype = sz
     L.gkrb200_sumcheck_prove.argtypes = [vp, vp, vp, i32, vp, sz, vp, sz, i32, vp, vp, vp, vp]
+    L.gkrb200_sumcheck_prove_device.argtypes = [vp, vp, vp, i32, vp, sz, vp, sz, i32, vp, vp, vp, vp]
+    L.gkrb200_check_mimc_circuit.argtypes = [i32, vp, vp, vp, vp]
     L.gkrb200_eq_table.argtypes = [vp, vp, sz, i32, vp, vp]
     L.gkrb200_fold.argtypes = [vp, vp, sz, vp, vp]
     L.gkrb200_round_eval.argtypes = [vp, vp, vp, vp, sz, i32, vp, vp]

@@ -54,6 +54,22 @@ class MimcCircuit:
     def __getitem__(self, l):
         return self.layers[l]
 
+    def check(self, arks=None):
+        """gkrb200_check_mimc_circuit on this description (what the Go shim does before Assign / gkr.Prove): raises GkrB200Error
+        unless it is examples.MimcCircuit().  arks: (94, 4) round constants per layer (default: hash.Arks in place)."""
+        import ctypes
+        import numpy as np
+        from .common import Ark
+        n_in = np.array([len(lay.In) for lay in self.layers], dtype=np.int32)
+        flat = np.array([p for lay in self.layers for p in lay.In] or [0], dtype=np.int32)
+        kinds = np.array([-1 if lay.gate_kind is None else lay.gate_kind for lay in self.layers], dtype=np.int32)
+        if arks is None:
+            arks = fr_empty(len(self.layers))
+            for l in range(3, min(len(self.layers), N_LAYERS)):
+                arks[l] = Ark(l - 3)
+        arks = fr_array(arks)
+        check(lib().gkrb200_check_mimc_circuit(len(self.layers), _p(n_in), _p(flat), _p(kinds), _p(arks)))
+
     def IsInputLayer(self, layer):
         return len(self.layers[layer].In) == 0
 
@@ -66,15 +82,21 @@ class MimcCircuit:
         sharded = world > 1 and (1 << bn) > world
         return bn, (n // world if sharded else n)
 
-    def Assign(self, key, msg, want_outputs=False):
-        """Circuit.Assign(inps...) (circuit/assignment.go:12-32).  key -> layer 0, msg -> layer 1."""
+    def Assign(self, key, msg, want_outputs=False, out=None):
+        """Circuit.Assign(inps...) (circuit/assignment.go:12-32).  key -> layer 0, msg -> layer 1.  want_outputs: a.outputs = a[93]
+        (this rank's shard when multi-GPU), copied back by the same call; `out` = caller's buffer for it (e.g. pinned memory)."""
         k = fr_array(key).reshape(-1, 4)
         m = fr_array(msg).reshape(-1, 4)
         if k.shape != m.shape:
             raise ValueError("inputs must have the same length")
         n = k.shape[0]
         bn, n_local = self._shape(n)
-        out93 = fr_empty(n_local) if want_outputs else None
+        out93 = None
+        if out is not None:
+            out93 = fr_array(out).reshape(-1, 4)[:n_local]
+            want_outputs = True
+        elif want_outputs:
+            out93 = fr_empty(n_local)
         check(lib().gkrb200_mimc_assign(self.ctx.handle, _p(k), _p(m), n, _p(out93)))
         a = Assignment(self.ctx, n_local, bn)
         if want_outputs:

@@ -47,3 +47,10 @@ def RandomFrArray(n):
     a = np.zeros((n, 4), dtype=np.uint64)
     a[:, 0] = v
     return ToMontgomery(a)
+
+
+def Ark(i):
+    """hash.Arks[i] (hash/ark.go:232-336), the constant of the cipher gate of layer i+3 (examples/mimc.go:29)"""
+    out = fr_empty()
+    check(lib().gkrb200_mimc_ark(i, _p(out)))
+    return out

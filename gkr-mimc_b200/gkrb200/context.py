@@ -36,10 +36,13 @@ class Context:
         check(lib().gkrb200_comm_unique_id(buf))
         return bytes(buf)
 
-    def comm_init(self, rank, world, unique_id):
+    def comm_init(self, rank, world, unique_id, leader=0):
+        """leader: the rank that runs the transcript of this communicator's proofs (same value on every rank)"""
         buf = (ctypes.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
         check(lib().gkrb200_comm_init(self._h, rank, world, buf))
         self.rank, self.world = rank, world
+        if world > 1:
+            check(lib().gkrb200_comm_set_leader(self._h, leader))
 
     @property
     def exchange_mode(self):
@@ -74,7 +77,7 @@ class Context:
     def set_profiling(self, on):
         check(lib().gkrb200_set_profiling(self._h, 1 if on else 0))
 
-    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN, OPT_CF_BLOCKS_PER_SM, OPT_EXCHANGE = 1, 2, 3, 4, 5
+    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN, OPT_CF_BLOCKS_PER_SM, OPT_EXCHANGE, OPT_INLINE_MIN_PAIRS, OPT_TRANSCRIPT = 1, 2, 3, 4, 5, 6, 7
 
     def set_option(self, option, value):
         check(lib().gkrb200_set_option(self._h, option, int(value)))

@@ -27,6 +27,23 @@ def Prove(ctx, X, qPrimes, claims, gate):
     return proof, chal, fin
 
 
+def ProveDevice(ctx, d_X, qPrimes, claims, gate):
+    """sumcheck.Prove with the tables already resident on the device: d_X = raw device pointers (Go layout, 2^bn entries each)"""
+    import ctypes
+    q = fr_array(qPrimes)
+    n_q, bn = q.shape[0], q.shape[1]
+    cl = fr_array(claims).reshape(-1, 4) if claims is not None and len(claims) else None
+    n_claims = 0 if cl is None else cl.shape[0]
+    nco = gate.Degree() + 2
+    nin = 2 if gate.kind == GATE_CIPHER else 1
+    proof, chal, fin = fr_empty(bn, nco), fr_empty(bn), fr_empty(1 + nin)
+    ark = fr_array(gate.ark) if gate.ark is not None else None
+    x1 = ctypes.c_void_p(d_X[1]) if gate.kind == GATE_CIPHER else None
+    check(lib().gkrb200_sumcheck_prove_device(ctx.handle, ctypes.c_void_p(d_X[0]), x1, bn, _p(q), n_q, _p(cl), n_claims, gate.kind, _p(ark),
+                                              _p(proof), _p(chal), _p(fin)))
+    return proof, chal, fin
+
+
 def PartialEvals(ctx, eq, X, gate):
     """one call of getPartialPolyChunk over the whole table (sumcheck/algo.go:54-205)"""
     e = fr_array(eq).reshape(-1, 4)

@@ -60,6 +60,9 @@ void gkrb200_free(gkrb200_ctx *ctx);
  * ncclUniqueId produced by gkrb200_comm_unique_id on rank 0 and broadcast by the caller.               */
 int gkrb200_comm_unique_id(uint8_t id_out[128]);
 int gkrb200_comm_init(gkrb200_ctx *ctx, int rank, int world, const uint8_t nccl_unique_id[128]);
+/* Which rank runs the Fiat-Shamir transcript of this communicator's proofs (default 0; set identically on every rank).
+ * "the transcript, interpolation and the layer loop ... run once, broadcast".                   */
+int gkrb200_comm_set_leader(gkrb200_ctx *ctx, int leader_rank);
 /* how the per-round partial sums travel between the ranks: 0 = exchange window (host-shared mapped memory written by the
  * round kernels themselves), 1 = NCCL all-gather, -1 = single GPU (see GKRB200_OPT_EXCHANGE)                       */
 int gkrb200_comm_exchange_mode(gkrb200_ctx *ctx);
@@ -120,6 +123,18 @@ int gkrb200_sumcheck_prove(gkrb200_ctx *ctx, const uint64_t *X0, const uint64_t 
                            const uint64_t *claims, size_t n_claims, int gate_kind, const uint64_t *ark, uint64_t *proof_out,
                            uint64_t *challenges_out, uint64_t *final_claims_out);
 
+/* Same with the tables already resident on the device (Go layout); they are not modified.                */
+int gkrb200_sumcheck_prove_device(gkrb200_ctx *ctx, const void *d_X0, const void *d_X1, int bn, const uint64_t *qprimes, size_t n_q,
+                                  const uint64_t *claims, size_t n_claims, int gate_kind, const uint64_t *ark, uint64_t *proof_out,
+                                  uint64_t *challenges_out, uint64_t *final_claims_out);
+
+/* ---- circuit.Circuit / BuildCircuit / IsInputLayer (circuit/circuit.go:11-91) -------------------------------
+ * The library proves examples.MimcCircuit() only.  The shim passes the description of the Circuit it was given: per layer the
+ * number of inputs n_in[l] (0 = input layer), the flattened In lists in_flat (sum of n_in entries), the gate kind
+ * gate_kinds[l] (-1 for an input layer, else GKRB200_GATE_*) and arks[l] (4 words per layer; read for cipher layers only).
+ * Returns 0 when it IS the MiMC circuit (examples/mimc.go:10-37), GKRB200_ERR_ARG (message says what differs) otherwise.     */
+int gkrb200_check_mimc_circuit(int n_layers, const int *n_in, const int *in_flat, const int *gate_kinds, const uint64_t *arks);
+
 /* ---- building blocks (each is one device kernel; used by tests, benches and other callers) ----------- */
 /* poly.FoldedEqTable / ChunkOfEqTable (poly/eq.go:41-89) and the multi-claim combination of
  * sumcheck/prover.go:121-141: out[x] = sum_j mult_j * eq(q_j, x); multipliers NULL => single table, seed 1 */
@@ -170,6 +185,7 @@ typedef struct {
     uint64_t bytes_round;         /* algorithmic bytes moved by the round kernels                        */
     uint64_t h2d_bytes;           /* bytes copied host->device / device->host by the library             */
     uint64_t d2h_bytes;
+    double follow_wait_ms;        /* multi-GPU follower ranks: host time asleep waiting for the leader's layer headers */
 } gkrb200_stats;
 int gkrb200_stats_reset(gkrb200_ctx *ctx);
 int gkrb200_stats_get(gkrb200_ctx *ctx, gkrb200_stats *out);
@@ -193,6 +209,15 @@ int gkrb200_set_profiling(gkrb200_ctx *ctx, int on);
  * collective, no extra launch); 1 = NCCL all-gather of the partials + a publishing kernel (A/B reference; also what
  * gkrb200_comm_init falls back to, on all ranks together, when /dev/shm cannot be mapped).                          */
 #define GKRB200_OPT_EXCHANGE 5
+/* GKRB200_OPT_INLINE_MIN_PAIRS (default 0): one-thread-per-pair rounds of the factored cipher kernel with at least this many
+ * pairs run the build with the multiplier inlined at every call site, smaller ones the out-of-line build (A/B of the
+ * call-ABI cost against instruction-cache footprint).                                            */
+#define GKRB200_OPT_INLINE_MIN_PAIRS 6
+/* GKRB200_OPT_TRANSCRIPT (multi-GPU, set identically on every rank): 0 (default) = ONE transcript per proof: the communicator's
+ * leader rank (gkrb200_comm_set_leader) hashes, the challenges reach every GPU through the exchange window and are consumed
+ * by device-side waits, follower ranks only enqueue kernels and sleep; 1 = every rank runs the transcript itself, in lockstep
+ * (round-1 behaviour, A/B reference; implied when the exchange is NCCL).                                                   */
+#define GKRB200_OPT_TRANSCRIPT 7
 int gkrb200_set_option(gkrb200_ctx *ctx, int option, long value);
 
 /* integer-pipe microbenchmarks for the roofline denominator: returns achieved rate.

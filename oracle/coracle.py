@@ -95,6 +95,26 @@ def fr_mul(a, b):
     return z
 
 
+def fr_mul_portable(a, b):
+    """the unsigned __int128 CIOS form (cross-check of the MULX/ADX multiplier)"""
+    a, b = _c(a), _c(b)
+    z = _fr()
+    lib().orc_fr_mul_portable(_p(a), _p(b), _p(z))
+    return z
+
+
+def fr_mul_kind():
+    lib().orc_fr_mul_kind.restype = ctypes.c_char_p
+    return lib().orc_fr_mul_kind().decode()
+
+
+def bench_fr_mul(iters=2_000_000):
+    """(ns per independent product, ns per dependent product) on one thread"""
+    out = (ctypes.c_double * 2)()
+    lib().orc_bench_fr_mul(ctypes.c_size_t(iters), out)
+    return float(out[0]), abs(float(out[1]))
+
+
 def fr_add(a, b):
     a, b = _c(a), _c(b)
     z = _fr()

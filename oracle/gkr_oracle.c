@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <time.h>
 #include <sched.h>
 #include <stdatomic.h>
 #include "fr.h"
@@ -123,6 +124,28 @@ int orc_get_threads(void) { return g_ncpu; }
 
 /* ------------------------------------------------------------------ field exports (tests) */
 void orc_fr_mul(const fr_t *a, const fr_t *b, fr_t *z) { fr_mul(z, a, b); }
+void orc_fr_mul_portable(const fr_t *a, const fr_t *b, fr_t *z) { fr_mul_portable(z, a, b); }
+const char *orc_fr_mul_kind(void) { return ORC_FR_MUL_KIND; }
+/* single-thread cost of one fr.Element.Mul in ns: [0] throughput form (4 independent chains), [1] latency form (one dependent chain) */
+void orc_bench_fr_mul(size_t iters, double out_ns[2]) {
+    struct timespec t0, t1;
+    fr_t a[4], b;
+    for (int k = 0; k < 4; k++) fr_set_u64(&a[k], 0x1234567 + (uint64_t)k);
+    fr_set_u64(&b, 0xabcdef01);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (size_t i = 0; i < iters; i++)
+        for (int k = 0; k < 4; k++) fr_mul(&a[k], &a[k], &b);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    out_ns[0] = ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / (4.0 * (double)iters);
+    fr_add(&b, &a[0], &a[1]);
+    fr_add(&b, &b, &a[2]);
+    fr_add(&b, &b, &a[3]);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (size_t i = 0; i < 4 * iters; i++) fr_mul(&b, &b, &b);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    out_ns[1] = ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / (4.0 * (double)iters);
+    if (fr_is_zero(&b)) out_ns[1] = -out_ns[1]; /* keeps the chain alive */
+}
 void orc_fr_add(const fr_t *a, const fr_t *b, fr_t *z) { fr_add(z, a, b); }
 void orc_fr_sub(const fr_t *a, const fr_t *b, fr_t *z) { fr_sub(z, a, b); }
 void orc_fr_inv(const fr_t *a, fr_t *z) { fr_inv(z, a); }

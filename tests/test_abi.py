@@ -187,3 +187,36 @@ def test_header_is_plain_c(tmp_path):
     hexval, veclen, _ = out.stdout.split(" ", 2)
     assert int(hexval, 16) == 1808205620575546259657963589762746470347087906694759866517376279978241663265  # hash/hash_test.go:21-27 through C
     assert int(veclen) == 1006 * 22 + 183
+
+
+def test_check_mimc_circuit_accepts_only_the_mimc_wiring():
+    """gkrb200_check_mimc_circuit (circuit/circuit.go:28-44 BuildCircuit / :70-79 IsInputLayer, examples/mimc.go:10-37): the Go shim
+    hands over the Circuit it was called with; anything but examples.MimcCircuit() is GKRB200_ERR_ARG with a message naming the layer."""
+    import gkrb200
+
+    class NoDevice:
+        world = 1
+
+    c = gkrb200.MimcCircuit(NoDevice())
+    c.check()  # the real circuit passes
+    for mutate, what in (
+            (lambda c: c.layers[50].In.__setitem__(1, 48), "layer 50 input 1"),         # wrong wiring
+            (lambda c: c.layers[3].In.reverse(), "layer 3 input 0"),                    # inputs swapped
+            (lambda c: setattr(c.layers[2], "gate_kind", 1), "layer 2 has gate kind"),  # identity layer given a cipher gate
+            (lambda c: c.layers[1].In.append(0), "layer 1 has 1 inputs"),               # an input layer with inputs
+            (lambda c: c.layers.pop(), "93 layers")):                                   # wrong depth
+        c = gkrb200.MimcCircuit(NoDevice())
+        mutate(c)
+        with pytest.raises(gkrb200.GkrB200Error) as e:
+            c.check()
+        assert e.value.code == -1 and what in str(e.value), str(e.value)
+    c = gkrb200.MimcCircuit(NoDevice())
+    arks = gkrb200.context.fr_empty(94)
+    for l in range(3, 94):
+        arks[l] = gkrb200.common.Ark(l - 3)
+    c.check(arks)
+    arks[40, 2] ^= np.uint64(1)
+    with pytest.raises(gkrb200.GkrB200Error) as e:
+        c.check(arks)
+    assert "layer 40" in str(e.value) and "Ark" in str(e.value)
+    assert gkrb200.lib().gkrb200_check_mimc_circuit(94, None, None, None, None) == -1

@@ -332,6 +332,11 @@ def test_gkr_2pow16_full_size_properties(ctx, oracle):
     c = gkrb200.MimcCircuit(ctx)
     a = c.Assign(key, msg, want_outputs=True)
     proof = gkrb200.gkr.Prove(c, a, qprime)
+    # gkr/gkr_test.go:14-78 at BASELINE config 3's size: hash outputs and EVERY word of the proof against the oracle
+    oracle.set_threads(os.cpu_count() or 1)
+    out93, evec = oracle.assign_and_prove_mimc(key, msg, qprime)
+    assert np.array_equal(a.outputs, out93), "hash outputs differ from the oracle"
+    assert np.array_equal(proof.to_vec(), evec), "proof differs from the oracle"
     assert oracle.gkr_verify_mimc(proof.to_vec(), key, msg, a.outputs, qprime) == 0
     assert np.array_equal(proof.Claims[1][0], oracle.evaluate(msg, proof.QPrimes[1][0]))
     assert np.array_equal(proof.Claims[2][45], oracle.evaluate(key, proof.QPrimes[2][45]))
@@ -348,9 +353,9 @@ def fast_fr(seed, n):
 
 @pytest.mark.parametrize("bn", [20, 22])
 def test_gkr_full_size_properties(oracle, bn):
-    """BASELINE configs 4/5 (2^20 and 2^22 hashes, all 93 layer tables resident): the proof is deterministic, the CPU oracle's
-    verifier and the device-backed verifier accept it and reject a corrupted one, sampled hash outputs equal the oracle's
-    MimcKeyedPermutation, and the input claims equal the oracle's MLE evaluations of the inputs."""
+    """BASELINE configs 4/5 (2^20 and 2^22 hashes, all 93 layer tables resident): every hash output and EVERY word of the proof
+    equal the oracle's (gkr/gkr_test.go:14-78 at size), the proof is deterministic, the CPU oracle's verifier and the
+    device-backed verifier accept it and reject a corrupted one, and the input claims equal the oracle's MLE evaluations."""
     import gkrb200
     n = 1 << bn
     big = gkrb200.Context(device=0, max_bn=bn)
@@ -363,6 +368,11 @@ def test_gkr_full_size_properties(oracle, bn):
         a2 = c.Assign(key, msg, want_outputs=True)
         proof2 = gkrb200.gkr.Prove(c, a2, qprime)
         assert np.array_equal(vec, proof2.to_vec()), "proof is not deterministic"
+        oracle.set_threads(os.cpu_count() or 1)
+        out93, evec = oracle.assign_and_prove_mimc(key, msg, qprime)
+        assert np.array_equal(a.outputs, out93), "hash outputs differ from the oracle"
+        assert np.array_equal(vec, evec), "proof differs from the oracle (word-for-word)"
+        del out93, evec
         idx = np.array([0, 1, n // 2 - 1, n // 2, n - 2, n - 1, 12345 % n, 777777 % n])
         for i in idx:
             assert np.array_equal(a.outputs[i], oracle.mimc_keyed_permutation(msg[i], key[i])), "hash output %d" % i

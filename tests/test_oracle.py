@@ -26,6 +26,29 @@ def test_field_constants():
     assert (r2 & (2**64 - 1)) == 0x1BB8E645AE216DA7
 
 
+def test_fast_multiplier_equals_portable_and_bigint(oracle):
+    """oracle/fr.h: the MULX/ADCX/ADOX product (the class of multiplier gnark-crypto's amd64 assembly is) against the textbook
+    unsigned __int128 CIOS form and against Python big ints, edge values and random"""
+    import random
+    rnd = random.Random(5)
+    R = (1 << 256) % Q
+    rinv = pow(R, -1, Q)
+    edge = [0, 1, 2, Q - 1, Q - 2, R, R * R % Q, Q // 2, Q // 2 + 1, (1 << 64) - 1, (1 << 128) - 1, (1 << 192) - 1, (1 << 253) - 1, Q - (1 << 64)]
+    vals = edge + [rnd.randrange(Q) for _ in range(200)]
+
+    def enc(v):
+        return np.array([(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+
+    for x in edge + vals[-20:]:
+        for y in vals:
+            got = oracle.fr_mul(enc(x), enc(y))
+            assert np.array_equal(got, oracle.fr_mul_portable(enc(x), enc(y)))
+            assert np.array_equal(got, enc(x * y * rinv % Q))
+    assert "CIOS" in oracle.fr_mul_kind()
+    thr, lat = oracle.bench_fr_mul(20000)
+    assert 0 < thr < 1e4 and 0 < lat < 1e4
+
+
 # ----------------------------------------------------------------- the reference's goldens
 def test_mimc_kat_reference_golden(oracle):
     """hash/hash_test.go:21-27 TestMimcCase"""

@@ -1,3 +1,5 @@
+// REJECTED EXPERIMENT (round 1), kept for the record: slower than the operand-scanning multiplier on B200 (profiles/r1_exp_karatsuba.txt).
+// Not part of the product build.
 // BN254 Fr multiplier, Karatsuba form: 48 + 72 wide multiply-adds per Montgomery product instead of 64 + 72,
 // and 48 instead of 64 for the plain 512-bit products the round sums accumulate.
 //
@@ -12,7 +14,7 @@
 // Everything here is __host__ __device__: tools/exp/kara_host_test.cu runs the same source on the CPU (portable
 // fallbacks of the carry-chain primitives) against the host multiplier of fr_host.hpp.
 #pragma once
-#include "fr_device.cuh"
+#include "../../gkr-mimc_b200/csrc/fr_device.cuh"
 
 namespace gkr {
 

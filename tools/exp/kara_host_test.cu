@@ -1,11 +1,11 @@
-// Host-side check of the Karatsuba multiplier (csrc/fr_kara.cuh, portable fallbacks) against the host multiplier
+// Host-side check of the Karatsuba multiplier (tools/exp/fr_kara.cuh, portable fallbacks) against the host multiplier
 // (csrc/fr_host.hpp) and a schoolbook 512-bit product.  Build: nvcc -O2 -std=c++17 -o /tmp/kara_host_test tools/exp/kara_host_test.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <random>
 #include <vector>
-#include "../../gkr-mimc_b200/csrc/fr_kara.cuh"
+#include "fr_kara.cuh"
 #include "../../gkr-mimc_b200/csrc/fr_host.hpp"
 namespace H = gkr::host;
 using gkr::Fr;

@@ -15,14 +15,19 @@ max_bn = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 ctx = gkrb200.Context(local, max(max_bn, 4))
 uid = [gkrb200.Context.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
-ctx.comm_init(rank, world, uid[0])
+leader = (world - 1) if len(sys.argv) > 2 and sys.argv[2] == "last" else 0
+ctx.comm_init(rank, world, uid[0], leader=leader)
 c = gkrb200.MimcCircuit(ctx)
 ok = True
 import time
-# every size through the exchange window (default), then again through the NCCL all-gather exchange (A/B)
-for mode, bn in [(0, b) for b in list(range(0, 9)) + [max_bn]] + [(1, b) for b in (2, 3, 5, 8, max_bn)]:
+# every size with ONE transcript per proof on the leader rank (default: window exchange, challenges consumed by device-side waits),
+# then the lockstep modes: every rank runs the transcript, round sums through the window / through NCCL all-gather (A/B)
+MODES = {0: "leader+window", 1: "lockstep+window", 2: "lockstep+nccl"}
+sizes = sorted(set(list(range(0, 9)) + [max_bn]))
+for mode, bn in [(0, b) for b in sizes] + [(1, b) for b in (2, 3, 5, 8, max_bn)] + [(2, b) for b in (2, 3, 5, 8, max_bn)]:
     if world > 1:
-        ctx.set_option(gkrb200.Context.OPT_EXCHANGE, mode)
+        ctx.set_option(gkrb200.Context.OPT_EXCHANGE, 1 if mode == 2 else 0)
+        ctx.set_option(gkrb200.Context.OPT_TRANSCRIPT, 0 if mode == 0 else 1)
     n = 1 << bn
     rng = np.random.default_rng(100 + bn)
     key = gkrb200.common.RandomFrArray(n); msg = key[::-1].copy(); q = gkrb200.common.RandomFrArray(bn + 1)[1:]
@@ -53,7 +58,7 @@ for mode, bn in [(0, b) for b in list(range(0, 9)) + [max_bn]] + [(1, b) for b i
     t = torch.tensor([1 if good else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("bn=%2d world=%d sharded=%s exchange=%s prove=%.1f ms : %s" % (bn, world, sharded, "nccl" if mode else "window", prove_ms,
+        print("bn=%2d world=%d sharded=%s mode=%s leader=%d prove=%.1f ms : %s" % (bn, world, sharded, MODES[mode], leader, prove_ms,
                                                                         "OK (bit-exact on all ranks)" if t.item() else "MISMATCH"), flush=True)
     ok = ok and bool(t.item())
 ctx.close()
