@@ -404,11 +404,11 @@ def main():
         assert np.array_equal(pr.to_vec(), ref_vec), "non-deterministic proof"
     # per-proof host breakdown, averaged over the proofs this rank LED (sharded: followers neither hash nor wait on rounds)
     led = [x for x in sts if x.rounds > 0]
-    n_led = max(1, sum(int(round(x.rounds / max(1, (1006 * bn + 183 - 183) // 1006 * 92))) for x in led)) if led else 1
-    rounds_per_proof = 92 * bn
+    rounds_per_proof = 92 * bn  # 91 cipher layers + the identity layer, bn rounds each
     n_led = max(1, int(round(sum(x.rounds for x in led) / max(1, rounds_per_proof)))) if led else 1
     brk = {"transcript_host": sum(x.transcript_ms for x in led) / n_led, "wait_device": sum(x.wait_ms for x in led) / n_led,
-           "comm_host": sum(x.comm_ms for x in led) / n_led, "rounds": rounds_per_proof, "proofs_led_by_rank0": n_led if led else 0}
+           "comm_host": sum(x.comm_ms for x in led) / n_led, "rounds": rounds_per_proof, "proofs_led_by_rank0": n_led if led else 0,
+           "follower_asleep_rank0": sum(x.follow_wait_ms for x in sts) / max(1, args.steps)}
 
     # e2e through the host-buffer API
     for i in range(P):

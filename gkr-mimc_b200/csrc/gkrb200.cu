@@ -134,7 +134,8 @@ struct gkrb200_ctx {
     FrRaw* d_local = nullptr;    // [64] this rank's contribution (multi-GPU); [16..19) residual entries of the last fold
     FrRaw* d_all = nullptr;      // [8*64]
     FrRaw* d_resid = nullptr;    // [3][TAIL_MAX] residual tables after the last device fold
-    int cf_blocks_per_sm1[2] = {CF_MINB1_FWD, CF_MINB1_FWD};
+    int cf_blocks_per_sm1[2] = {CF_MINB1_FWD, CF_MINB1_FWD};  // out-of-line build (128-thread blocks), NM = 7 / 8
+    int cf_blocks_per_sm_inl[2] = {2, 1};                       // inlined build (256-thread blocks)
     int cf_blocks_cap = 0;           // option: cap on the above (0 = none)
     uint32_t* partials_w = nullptr;  // 8 x 17 64-bit limb-column sums of the factored cipher round (zero between launches)
     int max_grid = 0;
@@ -329,14 +330,17 @@ static constexpr int CF_BLOCK = 128;  // PAR == 8 kernels
 static constexpr int CF_BLOCK1 = 128; // PAR == 1 kernels: 7-8 accumulators x 17 limbs x 128 threads = 61-70 KB of shared memory per block (64-thread blocks measured 30 % slower)
 static constexpr int CF_MINB1 = 3;    // -> 3 blocks (12 warps) per SM
 #ifndef GKR_CF_MINB_INL
-#define GKR_CF_MINB_INL 4
+#define GKR_CF_MINB_INL 2
 #endif
-static constexpr int CF_MINB_INL = GKR_CF_MINB_INL;  // register cap of the inlined-multiplier build (65536 / (128 * MINB)): 3 blocks are resident (shared memory), the rest of the register file stays free for the small kernels of other proofs in flight
+static constexpr int CF_MINB_INL = GKR_CF_MINB_INL;  // resident 256-thread blocks per SM of the inlined-multiplier build (=> 128 registers per thread)
 static constexpr int CF_MINB8 = 4;
 static constexpr int CF_WL1 = 17;   // limbs per accumulator, PAR == 1 (plain 512-bit products summed)
 static constexpr int CF_WL8 = 9;    // PAR == 8 (reduced products summed)
 static constexpr size_t CF_SMEM_PAR8 = (8 * 9 + (CF_BLOCK / 32) * 8 * 9 + (CF_BLOCK / 8) * 8 * 9) * 4;
-static inline size_t cf_smem(int nm, bool par8) { return par8 ? CF_SMEM_PAR8 : (size_t)nm * CF_WL1 * CF_BLOCK1 * 4; }
+static constexpr int CF_BLOCK_INL = 256;  // inlined-multiplier kernels: two 256-thread blocks (16 warps) per SM, 16-limb shared accumulators
+static inline size_t cf_smem_v(int nm, int variant) {  // variant: see CF_V_* below
+    return variant == 1 ? CF_SMEM_PAR8 : (variant == 0 ? (size_t)nm * 16 * CF_BLOCK_INL * 4 : (size_t)nm * CF_WL1 * CF_BLOCK1 * 4);
+}
 
 typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
 // variant: 0 = one thread per pair, multiplier inlined (big rounds); 1 = eight lanes per pair (small rounds);
@@ -344,7 +348,7 @@ typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
 enum { CF_V_INL = 0, CF_V_PAR8 = 1, CF_V_CALL = 2 };
 static cf_kernel_t cf_kernel(bool fold, int nm, int variant) {
     using namespace gkr;
-#define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK1, CF_MINB_INL, true>
+#define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK_INL, CF_MINB_INL, true>
 #define CF_K8(F, N) k_round_cf<F, N, 8, CF_BLOCK, CF_MINB8, false>
 #define CF_KC(F, N) k_round_cf<F, N, 1, CF_BLOCK1, CF_MINB1, false>
     static const cf_kernel_t tab[2][2][3] = {{{CF_K1(false, 7), CF_K8(false, 7), CF_KC(false, 7)}, {CF_K1(false, 8), CF_K8(false, 8), CF_KC(false, 8)}},
@@ -358,7 +362,7 @@ static int set_cf_attrs() {
     for (int f = 0; f < 2; f++)
         for (int n = 7; n <= 8; n++)
             for (int v = 0; v < 3; v++)
-                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem(n, v == CF_V_PAR8)));
+                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem_v(n, v)));
     return 0;
 }
 
@@ -403,6 +407,9 @@ static H::Fr wide_to_fr(const volatile uint64_t* w, int wl, int n_ranks, size_t 
 static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream);
 extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* stream) {
     if (!out || max_bn < 0 || max_bn > 26) return fail(GKRB200_ERR_ARG, "bad arguments to gkrb200_init (max_bn=%d)", max_bn);
+    // the host transcript's multiplier is MULX/ADCX/ADOX assembly (fr_host.hpp): refuse to start on a CPU without them instead of SIGILL
+    if (!__builtin_cpu_supports("adx") || !__builtin_cpu_supports("bmi2"))
+        return fail(GKRB200_ERR_STATE, "this host CPU lacks ADX/BMI2, which the Fiat-Shamir transcript's field multiplier needs");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -450,8 +457,10 @@ static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
     TRY(set_cf_attrs());
     for (int n = 7; n <= 8; n++) {  // resident blocks per SM of the PAR == 1 kernels (shared-memory bound): the grid is exactly one wave
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cf_kernel(true, n, CF_V_INL), CF_BLOCK1, cf_smem(n, false)));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cf_kernel(true, n, CF_V_CALL), CF_BLOCK1, cf_smem_v(n, CF_V_CALL)));
         c->cf_blocks_per_sm1[n - 7] = nb > 0 ? nb : 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, cf_kernel(true, n, CF_V_INL), CF_BLOCK_INL, cf_smem_v(n, CF_V_INL)));
+        c->cf_blocks_per_sm_inl[n - 7] = nb > 0 ? nb : 1;
     }
     return 0;
 }
@@ -1237,12 +1246,12 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         a.red.result = windowed(W) ? (unsigned long long*)xslot_d(tag, rank) : (W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result);
         a.red.seq = tag;
         a.red.chal = lead ? chal_wait(tag, k) : gkr::ChalWait{nullptr, nullptr, nullptr, 0};
-        const int blk = par8 ? CF_BLOCK : CF_BLOCK1;
-        int bps1 = cf_blocks_per_sm1[nm - 7];
+        const int variant = par8 ? CF_V_PAR8 : (half >= inline_min_pairs ? CF_V_INL : CF_V_CALL);
+        const int blk = par8 ? CF_BLOCK : (variant == CF_V_INL ? CF_BLOCK_INL : CF_BLOCK1);
+        int bps1 = variant == CF_V_INL ? cf_blocks_per_sm_inl[nm - 7] : cf_blocks_per_sm1[nm - 7];
         if (cf_blocks_cap > 0 && bps1 > cf_blocks_cap) bps1 = cf_blocks_cap;
         const int grid = grid_for(par8 ? half * 8 : half, blk, n_sm * (par8 ? CF_MINB8 : bps1));  // at most one resident wave
-        const int variant = par8 ? CF_V_PAR8 : (half >= inline_min_pairs ? CF_V_INL : CF_V_CALL);
-        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, variant), grid, blk, cf_smem(nm, par8), a);
+        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, variant), grid, blk, cf_smem_v(nm, variant), a);
         CUDA_TRY(cudaGetLastError());
         // algorithmic multiplier work in units of one Montgomery product (136 wide multiply-adds): 9 (NM = 8: 11) full products,
         // NM plain 512-bit products of 64 multiply-adds each, the eq factor product and four folds
@@ -1547,11 +1556,25 @@ static bool sumcheck_verify(const H::Fr* claims, size_t n_claims, const H::Fr* p
     return true;
 }
 
-extern "C" int gkrb200_gkr_verify_mimc(gkrb200_ctx* c, const uint64_t* proof_vec, int bn, const uint64_t* qprime, uint32_t flags) {
+// gkr.Verify(c, proof, inputs, outputs, qPrime).  io == nullptr: inputs/outputs are the ones of the assignment held by the context
+// (layers 0, 1, 93).  Otherwise io[0..2] = the caller's key, msg and outputs tables (host, 2^bn entries each), evaluated on the
+// device from the caller's bytes -- the form the hint's self-check needs (prover/gadget/hints.go:225-229: the solver's outputs, not
+// the prover's own recomputation, so a faulty assignment cannot vouch for itself).
+static int gkr_verify_common(gkrb200_ctx* c, const uint64_t* proof_vec, int bn, const uint64_t* qprime, uint32_t flags, const uint64_t* const* io) {
     if (!c || !proof_vec || (bn > 0 && !qprime)) return fail(GKRB200_ERR_ARG, "null argument");
-    if (c->bn < 0) return fail(GKRB200_ERR_STATE, "gkr_verify_mimc needs the assignment (inputs and outputs) in the context");
-    if (bn != c->bn) return fail(GKRB200_ERR_ARG, "inconsistent sizes : bn is %d but the assignment has 2^%d entries", bn, c->bn);
+    if (io) {
+        if (!io[0] || !io[1] || !io[2]) return fail(GKRB200_ERR_ARG, "null input/output table");
+        if (bn > c->cap_bn) return fail(GKRB200_ERR_OOM, "tables of 2^%d entries exceed this context's capacity 2^%d (a sharded context holds 1/world of a table)", bn, c->cap_bn);
+    } else {
+        if (c->bn < 0) return fail(GKRB200_ERR_STATE, "gkr_verify_mimc needs the assignment (inputs and outputs) in the context");
+        if (bn != c->bn) return fail(GKRB200_ERR_ARG, "inconsistent sizes : bn is %d but the assignment has 2^%d entries", bn, c->bn);
+    }
     CUDA_TRY(cudaSetDevice(c->device));
+    auto eval_io = [&](int which, int layer, const H::Fr* point, H::Fr* out) -> int {
+        if (!io) return c->mle_eval(c->slot(layer), bn, point, c->sharded, out);
+        TRY(c->upload(c->eq, io[which], (size_t)1 << bn));  // staged in the eq slot, folded into scratch[0]
+        return c->mle_eval(c->eq, bn, point, false, out);
+    };
     const size_t ubn = (size_t)bn, total = gkrb200_proof_vec_len(bn);
     std::vector<H::Fr> vec(total);
     memcpy(vec.data(), proof_vec, total * 32);
@@ -1567,7 +1590,7 @@ extern "C" int gkrb200_gkr_verify_mimc(gkrb200_ctx* c, const uint64_t* proof_vec
     if (bn && memcmp(qprime, qp[N_LAYERS - 1], ubn * 32) != 0) return fail(GKRB200_ERR_VERIFY, "initial qPrime does not match with the proof");
     // :36 the initial claim is the output MLE at qPrime (the prover does not send it)
     H::Fr out_claim;
-    TRY(c->mle_eval(c->slot(N_LAYERS - 1), bn, (const H::Fr*)qprime, c->sharded, &out_claim));
+    TRY(eval_io(2, N_LAYERS - 1, (const H::Fr*)qprime, &out_claim));
     std::vector<H::Fr> challenges(ubn + 1), tmp(MAX_CLAIMS);
     char why[160];
     for (int layer = N_LAYERS - 1; layer >= 0; layer--) {
@@ -1605,10 +1628,18 @@ extern "C" int gkrb200_gkr_verify_mimc(gkrb200_ctx* c, const uint64_t* proof_vec
     // testInitialRound (:120-132) for the two input layers
     for (int layer = 0; layer < 2; layer++) {
         H::Fr actual;
-        TRY(c->mle_eval(c->slot(layer), bn, qp[layer], c->sharded, &actual));
+        TRY(eval_io(layer, layer, qp[layer], &actual));
         if (!H::eq(actual, cl[layer][0])) return fail(GKRB200_ERR_VERIFY, "input layer check failed (layer %d)", layer);
     }
     return 0;
+}
+extern "C" int gkrb200_gkr_verify_mimc(gkrb200_ctx* c, const uint64_t* proof_vec, int bn, const uint64_t* qprime, uint32_t flags) {
+    return gkr_verify_common(c, proof_vec, bn, qprime, flags, nullptr);
+}
+extern "C" int gkrb200_gkr_verify_mimc_io(gkrb200_ctx* c, const uint64_t* proof_vec, int bn, const uint64_t* qprime, uint32_t flags, const uint64_t* key,
+                                          const uint64_t* msg, const uint64_t* outputs) {
+    const uint64_t* io[3] = {key, msg, outputs};
+    return gkr_verify_common(c, proof_vec, bn, qprime, flags, io);
 }
 
 // ------------------------------------------------------------------------------------------------ sumcheck.Prove on host tables
@@ -1730,7 +1761,7 @@ extern "C" int gkrb200_round_eval(gkrb200_ctx* c, const uint64_t* eq, const uint
 }
 
 extern "C" int gkrb200_fr_batch(gkrb200_ctx* c, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
-    if (!c || !a || !out || op < 0 || op > 3 || (op != 3 && !b) || n == 0) return fail(GKRB200_ERR_ARG, "bad argument");
+    if (!c || !a || !out || op < 0 || op > 4 || (op < 3 && !b) || n == 0) return fail(GKRB200_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     FrRaw* d = nullptr;
     CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(FrRaw)));

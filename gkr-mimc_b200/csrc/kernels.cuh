@@ -571,6 +571,62 @@ __device__ __forceinline__ void grid_reduce_wide_raw(uint32_t* sm, const WideOut
     grid_stage_wide<NM, WL, BLOCK>(sm, sm + NM * WL, out);
 }
 
+// INL layout: 16-limb accumulators in shared memory (sm[(k*16+l)*BLOCK + tid]) + each thread's overflow counts in the bytes of
+// `ovf`.  The block tree adds 512-bit numbers, so it too can carry out of limb 15: those carries join the executing thread's
+// counts, which are then summed over the block (warp shuffles + shared atomics) into limb 16 of the totals.
+template <int NM, int BLOCK>
+__device__ __forceinline__ void grid_reduce_wide_raw16(uint32_t* sm, unsigned long long ovf, const WideOut& out) {
+    const int tid = threadIdx.x;
+    __shared__ unsigned int s_cnt[8];
+    if (tid < 8) s_cnt[tid] = 0;
+    __syncthreads();
+    GKR_T(4);
+#pragma unroll 1
+    for (int stride = BLOCK / 2; stride >= 1; stride >>= 1) {
+        const int items = NM * stride;
+#pragma unroll 1
+        for (int it = tid; it < items; it += BLOCK) {
+            const int k = it / stride, i = it - k * stride;
+            uint32_t x[16], y[16];
+#pragma unroll
+            for (int l = 0; l < 16; l++) {
+                x[l] = sm[(k * 16 + l) * BLOCK + i];
+                y[l] = sm[(k * 16 + l) * BLOCK + i + stride];
+            }
+            uint32_t c = add8_carry(x, y);
+            c = add8_carry_in(x + 8, y + 8, c);
+            ovf += (unsigned long long)c << (8 * k);
+#pragma unroll
+            for (int l = 0; l < 16; l++) sm[(k * 16 + l) * BLOCK + i] = x[l];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < NM; k++) {
+        unsigned int c = (unsigned int)(ovf >> (8 * k)) & 0xffu;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if ((tid & 31) == 0 && c) atomicAdd(&s_cnt[k], c);
+    }
+    // compact the block totals (column 0 of every row + the counts) to the front as 17-limb numbers, then reuse the rest as scratch
+    constexpr int PER = (NM * 16 + BLOCK - 1) / BLOCK;
+    uint32_t v[PER];
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const int i = tid + j * BLOCK;
+        v[j] = i < NM * 16 ? sm[i * BLOCK] : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < PER; j++) {
+        const int i = tid + j * BLOCK;
+        if (i < NM * 16) sm[(i >> 4) * 17 + (i & 15)] = v[j];
+    }
+    if (tid < NM) sm[tid * 17 + 16] = s_cnt[tid];
+    __syncthreads();
+    grid_stage_wide<NM, 17, BLOCK>(sm, sm + NM * 17, out);
+}
+
 // Suffix eq tables of one layer's challenge vector q[0..n): block 0 builds the stages of the low part
 // v = q[n-c : n] (seeded with `seed`, the multi-GPU shard factor), block 1 those of the high part v = q[1 : n-c].
 // Stage j (j = 0..nv) = eq(last j variables of v, .) with 2^j entries at out[2^j .. 2^(j+1)), built by doubling
@@ -634,9 +690,30 @@ __device__ __forceinline__ Fr cf_mul(const Fr& a, const Fr& b) {
     return fr_mulc(a, b);
 }
 template <bool INL>
-__device__ __forceinline__ void cf_acc(uint32_t* acc, int stride, const Fr& a, const Fr& b) {
-    if (INL) fr_mul_acc_wide_inl(acc, stride, a, b);
-    else fr_mul_acc_wide(acc, stride, a, b);
+__device__ __forceinline__ Fr cf_sqr(const Fr& a) {
+    if (INL) return fr_sqr(a);
+    return fr_mulc(a, a);
+}
+// INL: the accumulator K keeps 16 limbs in shared memory and its overflow count (limb 16: at most 15 for 2^25 pairs per launch)
+// in byte K of the packed register `ovf` -- 448 instead of 476 bytes of shared memory per thread, which is what lets 16 instead of 12
+// warps be resident per SM (two 256-thread blocks).  !INL: 17 limbs in shared memory, out-of-line product.
+template <bool INL, int K>
+__device__ __forceinline__ void cf_acc(uint32_t* sm, int tid, int block, unsigned long long& ovf, const Fr& a, const Fr& b) {
+    if (INL) {
+        uint32_t* acc = sm + (size_t)K * 16 * block + tid;
+        uint32_t p[16];
+        fr_mul_wide(p, a, b);
+        uint32_t w[16];
+#pragma unroll
+        for (int l = 0; l < 16; l++) w[l] = acc[l * block];
+        uint32_t c = add8_carry(w, p);
+        c = add8_carry_in(w + 8, p + 8, c);
+        ovf += (unsigned long long)c << (8 * K);
+#pragma unroll
+        for (int l = 0; l < 16; l++) acc[l * block] = w[l];
+    } else {
+        fr_mul_acc_wide(sm + (size_t)K * 17 * block + tid, block, a, b);
+    }
 }
 
 template <bool FOLD, int NM, int PAR, int BLOCK, int MINB, bool INL>
@@ -646,10 +723,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
     extern __shared__ uint32_t sm[];  // PAR == 1: NM * 17 * BLOCK words; PAR == 8: see CF_SMEM_PAR8
     const int tid = threadIdx.x;
     GKR_T(0);
-    constexpr int WL1 = 17;  // limbs of a PAR == 1 accumulator (sum of plain 512-bit products)
+    constexpr int WL1 = 17;          // limbs of a PAR == 1 sum (plain 512-bit products added up)
+    constexpr int WLS = INL ? 16 : 17;  // of which in shared memory
+    unsigned long long ovf = 0;      // INL: the 17th limbs, one byte per accumulator
     if (PAR == 1) {
 #pragma unroll 1
-        for (int i = tid; i < NM * WL1 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
+        for (int i = tid; i < NM * WLS * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
     }
     GKR_T(1);
     const Fr r = (FOLD && a.r_dev) ? fr_load(a.r_dev) : fr_unpack(a.r);
@@ -695,7 +774,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
             // accumulated UNREDUCED (fr_mul_acc_wide).  9 Montgomery products per pair instead of 11 for powers + chain.
             Fr v30, v21, v12, v03;
             {
-                const Fr a2 = cf_mul<INL>(av, av), b2 = cf_mul<INL>(bv, bv);
+                const Fr a2 = cf_sqr<INL>(av), b2 = cf_sqr<INL>(bv);
                 v30 = cf_mul<INL>(a2, av);
                 v21 = cf_mul<INL>(a2, bv);
                 v12 = cf_mul<INL>(av, b2);
@@ -703,20 +782,20 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
             }
             if (NM == 8) {  // m_7 = (T b * b^3) * b^3
                 const Fr tb4 = cf_mul<INL>(cf_mul<INL>(u, bv), v03);
-                cf_acc<INL>(sm + (size_t)7 * WL1 * BLOCK + tid, BLOCK, tb4, v03);
+                cf_acc<INL, 7>(sm, tid, BLOCK, ovf, tb4, v03);
             }
             u = cf_mul<INL>(u, av);  // T a
             {
                 const Fr u1 = cf_mul<INL>(u, v03);  // T a b^3
-                cf_acc<INL>(sm + (size_t)4 * WL1 * BLOCK + tid, BLOCK, u1, v21);
-                cf_acc<INL>(sm + (size_t)5 * WL1 * BLOCK + tid, BLOCK, u1, v12);
-                cf_acc<INL>(sm + (size_t)6 * WL1 * BLOCK + tid, BLOCK, u1, v03);
+                cf_acc<INL, 4>(sm, tid, BLOCK, ovf, u1, v21);
+                cf_acc<INL, 5>(sm, tid, BLOCK, ovf, u1, v12);
+                cf_acc<INL, 6>(sm, tid, BLOCK, ovf, u1, v03);
             }
             u = cf_mul<INL>(u, v30);  // T a^4
-            cf_acc<INL>(sm + (size_t)3 * WL1 * BLOCK + tid, BLOCK, u, v03);
-            cf_acc<INL>(sm + (size_t)2 * WL1 * BLOCK + tid, BLOCK, u, v12);
-            cf_acc<INL>(sm + (size_t)1 * WL1 * BLOCK + tid, BLOCK, u, v21);
-            cf_acc<INL>(sm + tid, BLOCK, u, v30);
+            cf_acc<INL, 3>(sm, tid, BLOCK, ovf, u, v03);
+            cf_acc<INL, 2>(sm, tid, BLOCK, ovf, u, v12);
+            cf_acc<INL, 1>(sm, tid, BLOCK, ovf, u, v21);
+            cf_acc<INL, 0>(sm, tid, BLOCK, ovf, u, v30);
         }
     } else {
         const int j = tid & 7;
@@ -812,7 +891,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
         grid_stage_wide<NM, 9, BLOCK>(tot, sm + 8 * 9 + NW * 8 * 9, a.red);
         return;
     }
-    grid_reduce_wide_raw<NM, WL1, BLOCK>(sm, a.red);
+    if (INL) grid_reduce_wide_raw16<NM, BLOCK>(sm, ovf, a.red);
+    else grid_reduce_wide_raw<NM, WL1, BLOCK>(sm, a.red);
 }
 
 // copies n tagged 64-bit words (see publish_word) to mapped host memory; the tags travel with the data
@@ -883,12 +963,13 @@ __global__ void __launch_bounds__(256) k_fr_batch(int op, const FrRaw* __restric
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const Fr x = fr_load(a + i);
         Fr y = fr_zero();
-        if (op != 3) y = fr_load(b + i);
+        if (op != 3 && op != 4) y = fr_load(b + i);
         Fr z;
         switch (op) {
             case 0: z = fr_mul(x, y); break;
             case 1: z = fr_add(x, y); break;
             case 2: z = fr_sub(x, y); break;
+            case 4: z = fr_sqr(x); break;
             default: z = fr_pow7(x); break;
         }
         fr_store(out + i, z);

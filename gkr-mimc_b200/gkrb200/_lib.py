@@ -86,6 +86,7 @@ def lib():
     L.gkrb200_mle_evaluate.argtypes = [vp, vp, sz, vp, vp]
     L.gkrb200_assign_layer_evaluate.argtypes = [vp, i32, vp, i32, vp]
     L.gkrb200_gkr_verify_mimc.argtypes = [vp, vp, i32, vp, u32]
+    L.gkrb200_gkr_verify_mimc_io.argtypes = [vp, vp, i32, vp, u32, vp, vp, vp]
     L.gkrb200_set_option.argtypes = [vp, i32, ctypes.c_long]
     L.gkrb200_microbench.argtypes = [vp, i32, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = L

@@ -41,11 +41,19 @@ def Prove(c, a, qPrime, regular=False):
     return Proof(c, bn, vec)
 
 
-def Verify(c, a, proof, qPrime, regular=False):
-    """gkr.Verify(c, proof, inputs, outputs, qPrime) (gkr/verifier.go:15-59) against the assignment held by c.ctx (inputs = layers
-    0 and 1, outputs = layer 93, evaluated on the device).  Returns None when the proof is accepted, raises GkrB200Error otherwise
-    (the reference returns an error value)."""
-    bn = a.bn
+def Verify(c, a, proof, qPrime, regular=False, inputs=None, outputs=None):
+    """gkr.Verify(c, proof, inputs, outputs, qPrime) (gkr/verifier.go:15-59).  Without inputs/outputs: against the assignment held by
+    c.ctx (inputs = layers 0 and 1, outputs = layer 93, evaluated on the device).  With inputs=[key, msg] and outputs given (host
+    tables, the reference's own arguments): evaluated from the caller's bytes, independent of the prover's assignment.
+    Returns None when the proof is accepted, raises GkrB200Error otherwise (the reference returns an error value)."""
+    bn = a.bn if a is not None else (len(qPrime) if qPrime is not None else 0)
     q = fr_array(qPrime).reshape(-1, 4) if bn else None
     vec = fr_array(proof.to_vec() if isinstance(proof, Proof) else proof)
-    check(lib().gkrb200_gkr_verify_mimc(c.ctx.handle, _p(vec), bn, _p(q), PROOF_REGULAR if regular else PROOF_MONTGOMERY))
+    fl = PROOF_REGULAR if regular else PROOF_MONTGOMERY
+    if inputs is None and outputs is None:
+        check(lib().gkrb200_gkr_verify_mimc(c.ctx.handle, _p(vec), bn, _p(q), fl))
+        return
+    k, m, o = (fr_array(x).reshape(-1, 4) for x in (inputs[0], inputs[1], outputs))
+    if not (k.shape[0] == m.shape[0] == o.shape[0] == 1 << bn):
+        raise ValueError("inconsistent sizes : inputs/outputs must have 2^bn entries")
+    check(lib().gkrb200_gkr_verify_mimc_io(c.ctx.handle, _p(vec), bn, _p(q), fl, _p(k), _p(m), _p(o)))

@@ -105,6 +105,12 @@ int gkrb200_assign_layer_evaluate(gkrb200_ctx *ctx, int layer, const uint64_t *p
  * layers 0 and 1, outputs = layer 93, evaluated on the device).  proof_vec as produced by gkrb200_gkr_prove_mimc with the
  * same flags.  Returns 0 when the proof is accepted, GKRB200_ERR_VERIFY otherwise.                               */
 int gkrb200_gkr_verify_mimc(gkrb200_ctx *ctx, const uint64_t *proof_vec, int bn, const uint64_t *qprime, uint32_t flags);
+/* Same with the CALLER's inputs and outputs (host tables of 2^bn entries: key = inputs[0], msg = inputs[1], outputs), exactly the
+ * arguments of gkr.Verify(c, proof, inputs, outputs, qPrime) (gkr/verifier.go:15): their multilinear extensions are evaluated on
+ * the device from these bytes, so the check does not depend on the assignment the prover computed (the hint's self-check,
+ * prover/gadget/hints.go:225-229, passes the solver's outputs).  Not available on a sharded context (tables must fit one GPU).    */
+int gkrb200_gkr_verify_mimc_io(gkrb200_ctx *ctx, const uint64_t *proof_vec, int bn, const uint64_t *qprime, uint32_t flags,
+                               const uint64_t *key, const uint64_t *msg, const uint64_t *outputs);
 
 /* ---- gkr.Prove(c, a, qPrime)  (gkr/prover.go:21-91) for the MiMC circuit --------------------------------
  * Uses the assignment held by ctx.  proof_vec_out receives 1006*bn+183 elements in the order of

@@ -51,6 +51,11 @@ def test_device_field_ops_match_oracle(ctx, oracle):
         got = ctx.fr_batch(op, a, b)
         exp = np.stack([f(a[i], b[i]) for i in range(a.shape[0])])
         assert np.array_equal(got, exp), "op %d" % op
+    # fr.Element.Square: the dedicated squaring (36 + 72 wide multiply-adds) against the oracle's product, every edge value
+    got = ctx.fr_batch(4, a)
+    for i in list(range(0, len(e) * len(e), len(e) + 1)) + list(range(len(e) * len(e), a.shape[0], 3)):
+        assert np.array_equal(got[i], oracle.fr_mul(a[i], a[i])), "square %d" % i
+    assert np.array_equal(got, ctx.fr_batch(0, a, a)), "Square(a) != Mul(a, a)"
     got = ctx.fr_batch(3, a)
     for i in range(0, a.shape[0], 7):
         x2 = oracle.fr_mul(a[i], a[i])
@@ -584,3 +589,14 @@ def test_device_backed_verifier_accepts_and_rejects(ctx, oracle, bn):
     if bn:
         with pytest.raises(gkrb200.GkrB200Error):
             gkrb200.gkr.Verify(c, a, proof, rand_fr(rng, bn))  # another qPrime
+    # gkr.Verify(c, proof, inputs, outputs, qPrime) with the CALLER's tables (gkr/verifier.go:15, hints.go:225-229): accepts the
+    # true inputs/outputs; a wrong output or input is caught although the assignment in the context is intact
+    gkrb200.gkr.Verify(c, None, proof, qprime, inputs=[key, msg], outputs=a.outputs)
+    for which in range(3):
+        tabs = [key.copy(), msg.copy(), a.outputs.copy()]
+        tabs[which][(n - 1) // 2, 0] ^= np.uint64(1)
+        assert oracle.gkr_verify_mimc(vec, tabs[0], tabs[1], tabs[2], qprime) != 0
+        with pytest.raises(gkrb200.GkrB200Error) as e:
+            gkrb200.gkr.Verify(c, None, proof, qprime, inputs=tabs[:2], outputs=tabs[2])
+        assert e.value.code == -6
+    gkrb200.gkr.Verify(c, a, proof, qprime)  # the context's own assignment was not disturbed

@@ -91,3 +91,123 @@ def test_sharded_sumcheck_equals_single(kind, bn, world):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, bn, kind, q, out), nprocs=world, join=True)
     assert dict(out) == {g: 1 for g in range(world)}
+
+
+def _upload_worker(rank, world, port, n, out):
+    """stage_inputs in gkrb200.cu: each rank holds only its CONTIGUOUS 1/world slice of the table, de-interleaves it by owner
+    (k_destripe: send[d][j] = slice[j*world + d]) and the ranks swap the blocks (NCCL send/recv there, gloo here)."""
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        table = torch.arange(n, dtype=torch.int64) * 1000003 + 17
+        nl = n // world
+        blk = nl // world
+        mine = table[rank * nl:(rank + 1) * nl]
+        send = torch.stack([mine[d::world] for d in range(world)])  # send[d][j] = slice[j*world + d]
+        assert send.shape == (world, blk)
+        recv = torch.zeros((world, blk), dtype=torch.int64)
+        reqs = []
+        for peer in range(world):
+            if peer == rank:
+                recv[peer] = send[peer]
+                continue
+            reqs.append(dist.isend(send[peer].contiguous(), dst=peer))
+            reqs.append(dist.irecv(recv[peer], src=peer))
+        for r in reqs:
+            r.wait()
+        local = recv.reshape(-1)  # block from rank g lands at local[g*blk ...]
+        assert torch.equal(local, table[rank::world]), "re-strided shard differs from table[rank::world]"
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 16), (4, 64), (8, 64), (8, 512)])
+def test_sharded_upload_all_to_all(world, n):
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_upload_worker, args=(world, port, n, out), nprocs=world, join=True)
+    assert dict(out) == {g: 1 for g in range(world)}
+
+
+def _leader_worker(rank, world, port, bn, leader, q, out):
+    """One transcript per proof (gkrb200.cu lead_mode): every rank evaluates its shard, ONLY the leader interpolates and hashes,
+    the challenge travels back to all ranks (the exchange window + device-side wait on the GPUs, a broadcast here), followers
+    never call get_challenge; at the end the leader's layer header gives every rank the same proof."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyref as P
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        logw = world.bit_length() - 1
+        bnl = bn - logw
+        n = 1 << bn
+        gate = P.Gate("cipher", 145646)
+        tabs = [[(i * i + 3) % P.Q for i in range(n)], [(7 * i + 11) % P.Q for i in range(n)]]
+        X = [t[rank::world] for t in tabs]
+        s = 1
+        for b in range(logw):
+            qb = q[bn - 1 - b]
+            s = s * (qb if (rank >> b) & 1 else (1 - qb)) % P.Q
+        eq = P.folded_eq_table(q[:bnl], s)
+        hashes = 0
+
+        def to_leader(vals):
+            mine = _to_t(vals)
+            buf = [torch.zeros_like(mine) for _ in range(world)] if rank == leader else None
+            dist.gather(mine, buf, dst=leader)
+            return [_from_t(b) for b in buf] if rank == leader else None
+
+        def from_leader(vals, k):
+            t = _to_t(vals) if rank == leader else torch.zeros((k, 5), dtype=torch.int64)
+            dist.broadcast(t, src=leader)
+            return _from_t(t)
+
+        proof, chal = [], []
+        for _ in range(bnl):
+            parts = to_leader(P.partial_evals(eq, X, gate))
+            r = None
+            if rank == leader:
+                co = P.interpolate_on_range([sum(col) % P.Q for col in zip(*parts)])
+                r = P.get_challenge(co)
+                hashes += 1
+                proof.append(co)
+                chal.append(r)
+            r = from_leader([r] if rank == leader else None, 1)[0]
+            eq = P.fold(eq, r)
+            X = [P.fold(x, r) for x in X]
+        resid = to_leader([eq[0]] + [x[0] for x in X])
+        fin = None
+        if rank == leader:  # host tail on the leader only
+            eq = [resid[g][0] for g in range(world)]
+            X = [[resid[g][1 + k] for g in range(world)] for k in range(2)]
+            for _ in range(logw):
+                co = P.interpolate_on_range(P.partial_evals(eq, X, gate))
+                r = P.get_challenge(co)
+                hashes += 1
+                eq = P.fold(eq, r)
+                X = [P.fold(x, r) for x in X]
+                proof.append(co)
+                chal.append(r)
+            fin = [eq[0]] + [x[0] for x in X]
+        # the layer header: round polynomials, challenges, final claims -> every rank
+        flat = from_leader([c for co in proof for c in co] + chal + fin if rank == leader else None, bn * 9 + bn + 3)
+        got = ([flat[9 * k:9 * k + 9] for k in range(bn)], flat[9 * bn:10 * bn], flat[10 * bn:])
+        assert got == P.sumcheck_prove(tabs, [q], [], gate), "leader-transcript sumcheck differs from the single-device one"
+        assert hashes == (bn if rank == leader else 0)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bn,world,leader", [(5, 2, 0), (5, 2, 1), (4, 4, 3), (3, 8, 5)])
+def test_leader_transcript_equals_single(bn, world, leader):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyref as P
+    q = P.random_fr_array(bn + 2)[2:]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_leader_worker, args=(world, port, bn, leader, q, out), nprocs=world, join=True)
+    assert dict(out) == {g: 1 for g in range(world)}
