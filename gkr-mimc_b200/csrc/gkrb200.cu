@@ -337,7 +337,10 @@ static constexpr int CF_MINB8 = 4;
 static constexpr int CF_WL1 = 17;   // limbs per accumulator, PAR == 1 (plain 512-bit products summed)
 static constexpr int CF_WL8 = 9;    // PAR == 8 (reduced products summed)
 static constexpr size_t CF_SMEM_PAR8 = (8 * 9 + (CF_BLOCK / 32) * 8 * 9 + (CF_BLOCK / 8) * 8 * 9) * 4;
-static constexpr int CF_BLOCK_INL = 256;  // inlined-multiplier kernels: two 256-thread blocks (16 warps) per SM, 16-limb shared accumulators
+#ifndef GKR_CF_BLOCK_INL
+#define GKR_CF_BLOCK_INL 256
+#endif
+static constexpr int CF_BLOCK_INL = GKR_CF_BLOCK_INL;  // inlined-multiplier kernels: two 256-thread blocks (16 warps) per SM, 16-limb shared accumulators
 static inline size_t cf_smem_v(int nm, int variant) {  // variant: see CF_V_* below
     return variant == 1 ? CF_SMEM_PAR8 : (variant == 0 ? (size_t)nm * 16 * CF_BLOCK_INL * 4 : (size_t)nm * CF_WL1 * CF_BLOCK1 * 4);
 }

@@ -256,9 +256,23 @@ inline bool IsMimcCircuit(const circuit::Circuit& c) {
 }  // namespace examples
 
 namespace circuit {
+// What the Go shim does before Assign / gkr.Prove: the description of the Circuit it was called with goes to
+// gkrb200_check_mimc_circuit, which refuses (Panic, message names the layer) anything but examples.MimcCircuit().
+inline void CheckIsMimc(const Circuit& c) {
+    std::vector<int> n_in(c.size()), in, kinds(c.size());
+    std::vector<fr::Element> arks(c.size());
+    for (size_t l = 0; l < c.size(); l++) {
+        n_in[l] = (int)c[l].In.size();
+        in.insert(in.end(), c[l].In.begin(), c[l].In.end());
+        kinds[l] = c[l].gate.kind;
+        arks[l] = c[l].gate.ark;
+    }
+    in.push_back(0);
+    check(gkrb200_check_mimc_circuit((int)c.size(), n_in.data(), in.data(), kinds.data(), c.empty() ? nullptr : arks[0].data()));
+}
 // Circuit.Assign(inputs...) for examples.MimcCircuit(): inputs[0] = key (layer 0), inputs[1] = message block (layer 1)
 inline Assignment Assign(Device& d, const Circuit& c, const poly::MultiLin& key, const poly::MultiLin& msg) {
-    if (!examples::IsMimcCircuit(c)) throw Panic(GKRB200_ERR_ARG, "only examples.MimcCircuit() crosses the ABI");
+    CheckIsMimc(c);
     if (key.size() != msg.size()) throw Panic(GKRB200_ERR_ARG, "inconsistent input sizes");
     check(gkrb200_mimc_assign(d.handle(), key[0].data(), msg[0].data(), key.size(), nullptr));
     int bn = 0;
@@ -373,6 +387,7 @@ inline Proof ProofFromVec(const circuit::Circuit& c, int bn, const std::vector<f
 }
 // gkr.Prove(c, a, qPrime)
 inline Proof Prove(const circuit::Circuit& c, const circuit::Assignment& a, const std::vector<fr::Element>& qPrime) {
+    circuit::CheckIsMimc(c);
     std::vector<fr::Element> v(gkrb200_proof_vec_len(a.bn()));
     check(gkrb200_gkr_prove_mimc(a.device().handle(), detail::ptr(qPrime), (int)qPrime.size(), v[0].data(), GKRB200_PROOF_MONTGOMERY));
     return ProofFromVec(c, a.bn(), v);
@@ -382,6 +397,20 @@ inline Proof Prove(const circuit::Circuit& c, const circuit::Assignment& a, cons
 inline std::string Verify(const circuit::Circuit&, const Proof& proof, const circuit::Assignment& a, const std::vector<fr::Element>& qPrime) {
     const std::vector<fr::Element> v = GkrProofToVec(proof);
     const int rc = gkrb200_gkr_verify_mimc(a.device().handle(), v[0].data(), a.bn(), detail::ptr(qPrime), GKRB200_PROOF_MONTGOMERY);
+    if (rc == 0) return "";
+    if (rc == GKRB200_ERR_VERIFY) return gkrb200_last_error();
+    throw Panic(rc, gkrb200_last_error());
+}
+// gkr.Verify(c, proof, inputs, outputs, qPrime) with the CALLER's tables (gkr/verifier.go:15; the hint's self-check passes the solver's
+// outputs, prover/gadget/hints.go:225-229): their MLEs are evaluated on the device from these bytes, not from the prover's assignment.
+inline std::string Verify(Device& d, const circuit::Circuit& c, const Proof& proof, const std::vector<poly::MultiLin>& inputs, const poly::MultiLin& outputs,
+                          const std::vector<fr::Element>& qPrime) {
+    circuit::CheckIsMimc(c);
+    if (inputs.size() != 2 || inputs[0].size() != outputs.size() || inputs[1].size() != outputs.size() || outputs.size() != ((size_t)1 << qPrime.size()))
+        throw Panic(GKRB200_ERR_ARG, "inconsistent sizes of inputs / outputs / qPrime");
+    const std::vector<fr::Element> v = GkrProofToVec(proof);
+    const int rc = gkrb200_gkr_verify_mimc_io(d.handle(), v[0].data(), (int)qPrime.size(), detail::ptr(qPrime), GKRB200_PROOF_MONTGOMERY,
+                                              inputs[0][0].data(), inputs[1][0].data(), outputs[0].data());
     if (rc == 0) return "";
     if (rc == GKRB200_ERR_VERIFY) return gkrb200_last_error();
     throw Panic(rc, gkrb200_last_error());

@@ -105,6 +105,22 @@ static void TestCircuitShape() {
         threw = true;
     }
     EXPECT(threw, "BuildCircuit accepted an input layer with two consumers");
+    // the C side checks that the circuit it is asked to assign / prove IS examples.MimcCircuit() (gkrb200_check_mimc_circuit)
+    circuit::CheckIsMimc(c);
+    for (int variant = 0; variant < 4; variant++) {
+        circuit::Circuit w = examples::MimcCircuit();
+        if (variant == 0) w[50].In[1] = 48;                                    // wrong wiring
+        if (variant == 1) w[2].gate = gates::NewCipherGate(examples::Ark(0));  // wrong gate
+        if (variant == 2) w[7].gate.ark = examples::Ark(5);                    // wrong round constant
+        if (variant == 3) w.pop_back();                                        // wrong depth
+        threw = false;
+        try {
+            circuit::CheckIsMimc(w);
+        } catch (const Panic& p) {
+            threw = p.code == GKRB200_ERR_ARG;
+        }
+        EXPECT(threw, "CheckIsMimc accepted a circuit that is not the MiMC circuit (variant %d)", variant);
+    }
     // gate.Eval on scalars: cipher = (vL + vR + ark)^7
     const Element ark = fr::SetUint64(145646), l = fr::SetUint64(3), r = fr::SetUint64(4);
     Element t = fr::Add(fr::Add(l, r), ark), t7 = fr::One();
@@ -236,6 +252,14 @@ static void TestGKR(Device& d) {
         }
         const std::string err = gkr::Verify(c, proof, a, qPrime);
         EXPECT(err.empty(), "bn = %d error at gkr verifier : %s", bn, err.c_str());
+        // gkr.Verify(c, proof, inputs, outputs, qPrime) with the caller's tables (gkr_test.go:72): accepted; a wrong output is refused
+        {
+            poly::MultiLin outputs = a[93];
+            const std::string e2 = gkr::Verify(d, c, proof, {block, initstate}, outputs, qPrime);
+            EXPECT(e2.empty(), "bn = %d error at gkr verifier (caller's inputs/outputs) : %s", bn, e2.c_str());
+            outputs[outputs.size() / 2][0] ^= 1;
+            EXPECT(!gkr::Verify(d, c, proof, {block, initstate}, outputs, qPrime).empty(), "bn = %d: wrong outputs accepted", bn);
+        }
         // a tampered proof is refused
         gkr::Proof bad = proof;
         bad.Claims[40][0][0] ^= 1;
