@@ -200,6 +200,28 @@ struct gkrb200_ctx {
     int post_header(int layer, const H::Fr* coeffs, size_t n_coeffs, const H::Fr* challenges, int bn, const H::Fr* fin, int n_fin);
     int wait_header(int layer, H::Fr* coeffs, size_t n_coeffs, H::Fr* challenges, int bn, H::Fr* fin, int n_fin);
     int carve(size_t new_cap);
+    // grow-only device staging for the host-table entry points (sumcheck_prove, fold, round_eval, fr_batch, convert): a
+    // cudaMalloc/cudaFree pair per call costs tens of milliseconds at 64 MB (cudaFree synchronises the device)
+    FrRaw* io_buf = nullptr;
+    size_t io_cap = 0;
+    int io_reserve(size_t n_elems, FrRaw** out) {
+        if (n_elems > io_cap) {
+            if (io_buf) {
+                cudaStreamSynchronize(stream);
+                cudaFree(io_buf);
+                io_buf = nullptr;
+                io_cap = 0;
+            }
+            cudaError_t e = cudaMalloc(&io_buf, n_elems * sizeof(FrRaw));
+            if (e != cudaSuccess) {
+                io_buf = nullptr;
+                return fail(GKRB200_ERR_OOM, "cudaMalloc of a %.1f MiB staging buffer failed: %s", n_elems * 32.0 / (1 << 20), cudaGetErrorString(e));
+            }
+            io_cap = n_elems;
+        }
+        *out = io_buf;
+        return 0;
+    }
     int cap_bn = 0;  // log2(cap): what unsharded operations on this context can hold
 
     // instrumentation
@@ -452,7 +474,7 @@ static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
     memset(c->h_result, 0, 512 * sizeof(FrRaw));
     CUDA_TRY(cudaHostAlloc((void**)&c->h_stage, (size_t)MAX_CLAIMS * (max_bn + 2) * sizeof(H::Fr), cudaHostAllocDefault));
     // opt in to the dynamic shared memory the round kernels need
-    const int smem9 = 9 * 9 * ROUND_BLOCK * 4, smem3 = 3 * 9 * ROUND_BLOCK * 4;
+    const int smem9 = 9 * 9 * ROUND_BLOCK * 4, smem3 = 3 * 17 * ROUND_BLOCK * 4;
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem9));
     CUDA_TRY(cudaFuncSetAttribute(gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem3));
@@ -521,6 +543,7 @@ extern "C" void gkrb200_free(gkrb200_ctx* c) {
         cudaEventDestroy(e.b);
     }
     cudaFree(c->arena);
+    cudaFree(c->io_buf);
     cudaFree(c->ticket);
     cudaFreeHost(c->h_result);
     cudaFreeHost(c->h_stage);
@@ -995,6 +1018,7 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
     const int bnl = bn - LW;  // rounds run on the device
     const int nev = gate == gkr::GATE_CIPHER ? 9 : 3;
     const int nin = gate == gkr::GATE_CIPHER ? 2 : 1;
+    const int wl = gate == gkr::GATE_CIPHER ? 9 : 17;  // limbs per published sum: canonical values / unreduced sums of plain products
     const size_t n_local = (size_t)1 << bnl;
     const bool lead = lead_mode(W), am_leader = !lead || rank == leader;
 
@@ -1070,8 +1094,9 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         a.red.result = windowed(W) ? (unsigned long long*)xslot_d(tag, rank) : (W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result);
         a.red.seq = tag;
         a.red.chal = lead ? chal_wait(tag, k) : gkr::ChalWait{nullptr, nullptr, nullptr, 0};
+        a.partials_w = partials_w;
         const int grid = grid_for(half, ROUND_BLOCK, max_grid);
-        const size_t smem = (size_t)nev * 9 * ROUND_BLOCK * 4;
+        const size_t smem = (size_t)nev * wl * ROUND_BLOCK * 4;
         if (gate == gkr::GATE_CIPHER) {
             auto kf = do_fold ? gkr::k_round<gkr::GATE_CIPHER, true, ROUND_BLOCK, ROUND_MINB> : gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK, ROUND_MINB>;
             LAUNCH(this, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
@@ -1080,7 +1105,7 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         } else {
             auto kf = do_fold ? gkr::k_round<gkr::GATE_IDENTITY, true, ROUND_BLOCK, ROUND_MINB> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>;
             LAUNCH(this, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
-            st.fr_mul_round += (uint64_t)half * (3 + (do_fold ? 4 : 0));
+            st.fr_mul_round += (uint64_t)half * (3 * 64 + (do_fold ? 4 * 136 : 0)) / 136;  // three plain products (64 of 136 wide MACs each)
             st.bytes_round += (uint64_t)half * 32 * (do_fold ? (8 + 4) : 4);
         }
         CUDA_TRY(cudaGetLastError());
@@ -1091,7 +1116,7 @@ int gkrb200_ctx::sumcheck(const FrRaw* x0, const FrRaw* x1, int bn, const H::Fr*
         return 0;
     };
     auto transcript_round = [&](int k) -> int {
-        TRY(exchange_and_fetch_wide(nev, 9, W, tags[k], evals));
+        TRY(exchange_and_fetch_wide(nev, wl, W, tags[k], evals));
         const double t0 = now_ms();
         H::Fr* coeffs = proof_out + (size_t)k * nev;
         lagrange.interpolate(evals, nev, coeffs);  // poly/lagrange.go:96
@@ -1437,7 +1462,7 @@ extern "C" int gkrb200_convert(gkrb200_ctx* c, const uint64_t* in, size_t n, uin
     if (n == 0) return 0;
     CUDA_TRY(cudaSetDevice(c->device));
     FrRaw* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, n * sizeof(FrRaw)));
+    TRY(c->io_reserve(n, &d));
     int rc = c->upload(d, in, n);
     if (!rc) {
         LAUNCH(c, KC_STAGING, gkr::k_convert, grid_for(n, 256, c->n_sm * 8), 256, 0, d, d, n, to_mont ? 1 : 0);
@@ -1446,7 +1471,6 @@ extern "C" int gkrb200_convert(gkrb200_ctx* c, const uint64_t* in, size_t n, uin
         if (e != cudaSuccess) rc = fail(GKRB200_ERR_CUDA, "convert: %s", cudaGetErrorString(e));
         c->st.d2h_bytes += n * sizeof(FrRaw);
     }
-    cudaFree(d);
     return rc;
 }
 
@@ -1661,7 +1685,7 @@ static int sumcheck_prove_common(gkrb200_ctx* c, const void* X0, const void* X1,
     FrRaw* d = nullptr;
     int rc = 0;
     if (!on_device) {
-        CUDA_TRY(cudaMalloc(&d, 2 * n * sizeof(FrRaw)));
+        TRY(c->io_reserve(2 * n, &d));
         rc = c->upload(d, X0, n);
         if (!rc && gate_kind == GKRB200_GATE_CIPHER) rc = c->upload(d + n, X1, n);
         d0 = d;
@@ -1672,10 +1696,7 @@ static int sumcheck_prove_common(gkrb200_ctx* c, const void* X0, const void* X1,
     if (!rc)
         rc = c->sumcheck(d0, gate_kind == GKRB200_GATE_CIPHER ? d1 : nullptr, bn, (const H::Fr*)qprimes, n_q, (const H::Fr*)claims, n_claims,
                          gate_kind, a, false, (H::Fr*)proof_out, (H::Fr*)challenges_out, (H::Fr*)final_claims_out);
-    if (d) {
-        cudaStreamSynchronize(c->stream);
-        cudaFree(d);
-    }
+    if (d) cudaStreamSynchronize(c->stream);  // the caller's host tables may be released as soon as the call returns
     return rc;
 }
 extern "C" int gkrb200_sumcheck_prove(gkrb200_ctx* c, const uint64_t* X0, const uint64_t* X1, int bn, const uint64_t* qprimes, size_t n_q,
@@ -1706,7 +1727,7 @@ extern "C" int gkrb200_fold(gkrb200_ctx* c, const uint64_t* table, size_t n, con
     if (!table || !r || !out || n < 2) return fail(GKRB200_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     FrRaw* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, (n + n / 2) * sizeof(FrRaw)));
+    TRY(c->io_reserve(n + n / 2, &d));
     int rc = c->upload(d, table, n);
     if (!rc) {
         gkr::FoldArgs f{};
@@ -1720,7 +1741,6 @@ extern "C" int gkrb200_fold(gkrb200_ctx* c, const uint64_t* table, size_t n, con
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(GKRB200_ERR_CUDA, "fold: %s", cudaGetErrorString(e));
     }
-    cudaFree(d);
     return rc;
 }
 
@@ -1733,7 +1753,7 @@ extern "C" int gkrb200_round_eval(gkrb200_ctx* c, const uint64_t* eq, const uint
     if (gate_kind == GKRB200_GATE_CIPHER && !X1) return fail(GKRB200_ERR_ARG, "cipher gate needs two input tables");
     CUDA_TRY(cudaSetDevice(c->device));
     FrRaw* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(FrRaw)));
+    TRY(c->io_reserve(3 * n, &d));
     int rc = c->upload(d, eq, n);
     if (!rc) rc = c->upload(d + n, X0, n);
     if (!rc && gate_kind == GKRB200_GATE_CIPHER) rc = c->upload(d + 2 * n, X1, n);
@@ -1749,17 +1769,17 @@ extern "C" int gkrb200_round_eval(gkrb200_ctx* c, const uint64_t* eq, const uint
         a.red.ticket = c->ticket;
         a.red.result = (unsigned long long*)c->h_result;
         a.red.seq = c->seq;
-        const int nev = gate_kind == GKRB200_GATE_CIPHER ? 9 : 3;
+        const int nev = gate_kind == GKRB200_GATE_CIPHER ? 9 : 3, wl = gate_kind == GKRB200_GATE_CIPHER ? 9 : 17;
+        a.partials_w = c->partials_w;
         const int grid = grid_for(a.half, ROUND_BLOCK, c->max_grid);
-        const size_t smem = (size_t)nev * 9 * ROUND_BLOCK * 4;
+        const size_t smem = (size_t)nev * wl * ROUND_BLOCK * 4;
         auto kf = gate_kind == GKRB200_GATE_CIPHER ? gkr::k_round<gkr::GATE_CIPHER, false, ROUND_BLOCK, ROUND_MINB> : gkr::k_round<gkr::GATE_IDENTITY, false, ROUND_BLOCK, ROUND_MINB>;
         LAUNCH(c, KC_ROUND, kf, grid, ROUND_BLOCK, smem, a);
         H::Fr ev[MAX_EV];
-        rc = c->exchange_and_fetch_wide(nev, 9, 1, c->seq, ev);
+        rc = c->exchange_and_fetch_wide(nev, wl, 1, c->seq, ev);
         if (!rc) memcpy(evals_out, ev, (size_t)nev * 32);
     }
     cudaStreamSynchronize(c->stream);
-    cudaFree(d);
     return rc;
 }
 
@@ -1767,7 +1787,7 @@ extern "C" int gkrb200_fr_batch(gkrb200_ctx* c, int op, const uint64_t* a, const
     if (!c || !a || !out || op < 0 || op > 4 || (op < 3 && !b) || n == 0) return fail(GKRB200_ERR_ARG, "bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
     FrRaw* d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, 3 * n * sizeof(FrRaw)));
+    TRY(c->io_reserve(3 * n, &d));
     int rc = c->upload(d, a, n);
     if (!rc && b) rc = c->upload(d + n, b, n);
     if (!rc) {
@@ -1776,7 +1796,6 @@ extern "C" int gkrb200_fr_batch(gkrb200_ctx* c, int op, const uint64_t* a, const
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = fail(GKRB200_ERR_CUDA, "fr_batch: %s", cudaGetErrorString(e));
     }
-    cudaFree(d);
     return rc;
 }
 

@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(EQX_BLOCK) k_eq_expand(const FrRaw* __restrict
     __shared__ uint32_t acc[17 * EQX_BLOCK];
     const size_t mask = ((size_t)1 << nl) - 1;
     const int tid = threadIdx.x;
+    if (n_claims == 1) {  // poly.FoldedEqTable proper: one product per entry, one streaming write
+        for (size_t x = (size_t)blockIdx.x * blockDim.x + tid; x < n; x += (size_t)gridDim.x * blockDim.x)
+            fr_store(out + x, fr_mul(fr_load(hi + (x >> nl)), fr_load(lo + (x & mask))));
+        return;
+    }
     for (size_t x = (size_t)blockIdx.x * blockDim.x + tid; x < n; x += (size_t)gridDim.x * blockDim.x) {
         Fr total = fr_zero();
 #pragma unroll 1
@@ -206,12 +211,23 @@ struct FoldArgs {
 __global__ void __launch_bounds__(256) k_fold(const FoldArgs a) {
     const Fr r = a.r_dev ? fr_load(a.r_dev) : fr_unpack(a.r);
     const size_t total = a.half * (size_t)a.n_tables;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int t = (int)(i / a.half);
-        const size_t x = i - (size_t)t * a.half;
-        const Fr b = fr_load_stream(a.src[t] + x);
-        const Fr u = fr_load_stream(a.src[t] + x + a.half);
-        fr_store(a.dst[t] + x, fr_add(b, fr_mul(r, fr_sub(u, b))));
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    // two outputs per iteration, all four loads in flight before the first product: at 96 B per 136 wide multiply-adds the kernel
+    // sits at B200's ridge (6.5 TB/s / 8.1 T wide MAC/s = 0.8 B per MAC), so neither DRAM latency nor the multiplier may idle
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * step) {
+        const size_t i2 = i + step;
+        const bool two = i2 < total;
+        const int t = (int)(i / a.half), t2 = two ? (int)(i2 / a.half) : t;
+        const size_t x = i - (size_t)t * a.half, x2 = two ? i2 - (size_t)t2 * a.half : x;
+        // table pointers by selection, not by indexing the parameter arrays (that would copy them to local memory)
+        const FrRaw* s1 = t == 0 ? a.src[0] : (t == 1 ? a.src[1] : a.src[2]);
+        const FrRaw* s2 = t2 == 0 ? a.src[0] : (t2 == 1 ? a.src[1] : a.src[2]);
+        FrRaw* d1 = t == 0 ? a.dst[0] : (t == 1 ? a.dst[1] : a.dst[2]);
+        FrRaw* d2 = t2 == 0 ? a.dst[0] : (t2 == 1 ? a.dst[1] : a.dst[2]);
+        const Fr b = fr_load_stream(s1 + x), u = fr_load_stream(s1 + x + a.half);
+        const Fr b2 = fr_load_stream(s2 + x2), u2 = fr_load_stream(s2 + x2 + a.half);
+        fr_store(d1 + x, fr_add(b, fr_mul(r, fr_sub(u, b))));
+        if (two) fr_store(d2 + x2, fr_add(b2, fr_mul(r, fr_sub(u2, b2))));
     }
 }
 
@@ -230,6 +246,7 @@ struct RoundArgs {
     const FrRaw* r_dev;  // ... or, when not null, where a previous launch left it in device memory
     FrRaw ark;           // cipher gate constant
     ReduceOut red;
+    uint32_t* partials_w;  // identity gate: 64-bit limb-column sums of the wide (unreduced) round sums, zero between launches
 };
 
 template <int GATE>
@@ -371,51 +388,6 @@ __device__ __forceinline__ void grid_reduce_wide(uint32_t* sm, const ReduceOut& 
         publish_word(out.result + tid * 9 + 8, out.seq, 0u);
     }
     wait_challenge(out.chal);
-}
-
-template <int GATE, bool FOLD, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_round(const RoundArgs a) {
-    constexpr int NEV = GateTraits<GATE>::NEV;
-    extern __shared__ uint32_t sm[];  // NEV * 9 * BLOCK words
-    const int tid = threadIdx.x;
-#pragma unroll 1
-    for (int i = tid; i < NEV * 9 * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
-    const Fr r = a.r_dev ? fr_load(a.r_dev) : fr_unpack(a.r);
-
-    for (size_t x = (size_t)blockIdx.x * BLOCK + tid; x < a.half; x += (size_t)gridDim.x * BLOCK) {
-        Fr e, de, s, ds;
-        {
-            Fr e1;
-            load_pair<FOLD>(a.src[0], a.dst[0], x, a.half, r, e, e1);
-            de = fr_sub(e1, e);
-        }
-        if (GATE == GATE_CIPHER) {
-            // s_t = X0_t + X1_t + ark  (cipher.go:34-35): sum bottom and top values over the two input tables
-            Fr s1 = fr_unpack(a.ark);
-            s = s1;
-#pragma unroll 1
-            for (int tb = 1; tb <= 2; tb++) {
-                Fr b, t;
-                load_pair<FOLD>(a.src[tb], a.dst[tb], x, a.half, r, b, t);
-                s = fr_add(s, b);
-                s1 = fr_add(s1, t);
-            }
-            ds = fr_sub(s1, s);
-        } else {
-            Fr s1;
-            load_pair<FOLD>(a.src[1], a.dst[1], x, a.half, r, s, s1);
-            ds = fr_sub(s1, s);
-        }
-        // evals[t] += eq_t * gate(s_t), t = 0..NEV-1; (e,s) advance by the differences (algo.go:149-199)
-#pragma unroll 1
-        for (int t = 0; t < NEV; t++) {
-            const Fr term = fr_mul(e, GATE == GATE_CIPHER ? fr_pow7(s) : s);
-            wide_acc_add<BLOCK>(sm + (size_t)t * 9 * BLOCK + tid, term);
-            e = fr_add(e, de);
-            s = fr_add(s, ds);
-        }
-    }
-    grid_reduce_wide<NEV, BLOCK>(sm, a.red);
 }
 
 // ================================================================================================
@@ -625,6 +597,65 @@ __device__ __forceinline__ void grid_reduce_wide_raw16(uint32_t* sm, unsigned lo
     if (tid < NM) sm[tid * 17 + 16] = s_cnt[tid];
     __syncthreads();
     grid_stage_wide<NM, 17, BLOCK>(sm, sm + NM * 17, out);
+}
+
+// Identity gate (layer 2 of the MiMC circuit): the three products eq_t * X_t only feed the round sums, so they are accumulated as
+// PLAIN 512-bit products (64 instead of 136 wide multiply-adds each; the host applies one REDC per sum, exactly like the
+// factored cipher round) -- at 128 B per pair that moves the kernel from the multiplier's side of B200's ridge to the HBM side.
+template <int GATE, bool FOLD, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_round(const RoundArgs a) {
+    constexpr int NEV = GateTraits<GATE>::NEV;
+    constexpr bool WIDE = GATE == GATE_IDENTITY;
+    constexpr int WL = WIDE ? 17 : 9;
+    extern __shared__ uint32_t sm[];  // NEV * WL * BLOCK words
+    const int tid = threadIdx.x;
+#pragma unroll 1
+    for (int i = tid; i < NEV * WL * BLOCK; i += BLOCK) sm[i] = 0;  // own columns only (i % BLOCK == tid)
+    const Fr r = a.r_dev ? fr_load(a.r_dev) : fr_unpack(a.r);
+
+    for (size_t x = (size_t)blockIdx.x * BLOCK + tid; x < a.half; x += (size_t)gridDim.x * BLOCK) {
+        Fr e, de, s, ds;
+        {
+            Fr e1;
+            load_pair<FOLD>(a.src[0], a.dst[0], x, a.half, r, e, e1);
+            de = fr_sub(e1, e);
+        }
+        if (GATE == GATE_CIPHER) {
+            // s_t = X0_t + X1_t + ark  (cipher.go:34-35): sum bottom and top values over the two input tables
+            Fr s1 = fr_unpack(a.ark);
+            s = s1;
+#pragma unroll 1
+            for (int tb = 1; tb <= 2; tb++) {
+                Fr b, t;
+                load_pair<FOLD>(a.src[tb], a.dst[tb], x, a.half, r, b, t);
+                s = fr_add(s, b);
+                s1 = fr_add(s1, t);
+            }
+            ds = fr_sub(s1, s);
+        } else {
+            Fr s1;
+            load_pair<FOLD>(a.src[1], a.dst[1], x, a.half, r, s, s1);
+            ds = fr_sub(s1, s);
+        }
+        // evals[t] += eq_t * gate(s_t), t = 0..NEV-1; (e,s) advance by the differences (algo.go:149-199)
+#pragma unroll 1
+        for (int t = 0; t < NEV; t++) {
+            if (WIDE) {
+                fr_mul_acc_wide(sm + (size_t)t * WL * BLOCK + tid, BLOCK, e, s);
+            } else {
+                const Fr term = fr_mul(e, fr_pow7(s));
+                wide_acc_add<BLOCK>(sm + (size_t)t * 9 * BLOCK + tid, term);
+            }
+            e = fr_add(e, de);
+            s = fr_add(s, ds);
+        }
+    }
+    if (WIDE) {
+        const WideOut wo{a.partials_w, a.red.ticket, a.red.result, a.red.seq, a.red.chal};
+        grid_reduce_wide_raw<NEV, 17, BLOCK>(sm, wo);
+    } else {
+        grid_reduce_wide<NEV, BLOCK>(sm, a.red);
+    }
 }
 
 // Suffix eq tables of one layer's challenge vector q[0..n): block 0 builds the stages of the low part
