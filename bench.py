@@ -308,12 +308,15 @@ def main():
         P = args.inflight
     elif replicas:
         P = max(1, min(8, args.steps, cores // world))
+    elif sharded:
+        # one spinning/hashing host thread per proof in flight on the whole box (its leader); the other ranks' threads sleep on a futex
+        P = max(1, min(max(8, 3 * world), args.steps, cores - max(2, cores // 4)))
     else:
         P = max(1, min(8, args.steps, cores - 2))
     main_stream = torch.cuda.Stream()
     streams = [torch.cuda.Stream() for _ in range(P)]  # the library launches on these; events are recorded on main_stream after joining them
     torch.cuda.set_stream(main_stream)
-    ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream) for st_ in streams]
+    ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream, world=world if sharded else 1) for st_ in streams]
     ctx = ctxs[0]
     if sharded:
         for i, c in enumerate(ctxs):  # one communicator per pipeline, created in the same order on every rank

@@ -464,6 +464,42 @@ __device__ __forceinline__ Fr fr_sqr(const Fr& a) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// Product by a per-launch constant (the fold challenge r: every fold of a sumcheck round is r * (top - bottom)).
+// With K_i = r * 2^(32i+64) * 2^-256 mod q (eight canonical residues the host derives from r once per launch),
+//     sum_i d_i * K_i  ==  (r * d * 2^-256) * 2^64   (mod q),   d = sum_i d_i 2^(32i),
+// a 290-bit number built from 64 wide multiply-adds whose rows all start at limb 0; two Montgomery rows remove the factor
+// 2^64: 80 wide multiply-adds instead of 136, same canonical result as fr_mul(r, d).  K lives in the kernel's parameter
+// space, so its limbs reach the multiplier as constant-bank operands and cost no registers.
+// ---------------------------------------------------------------------------------------------
+struct FrConstMul {
+    uint32_t k[8][8];
+};
+__device__ __forceinline__ Fr fr_mul_const(const FrConstMul& K, const Fr& d) {
+    uint32_t P[11], Qd[10];
+#pragma unroll
+    for (int i = 0; i < 11; i++) P[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) Qd[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        chain4(P[0], P[1], P[2], P[3], P[4], P[5], P[6], P[7], P[8], K.k[i][0], K.k[i][2], K.k[i][4], K.k[i][6], d.v[i]);
+        chain4(Qd[1], Qd[2], Qd[3], Qd[4], Qd[5], Qd[6], Qd[7], Qd[8], Qd[9], K.k[i][1], K.k[i][3], K.k[i][5], K.k[i][7], d.v[i]);
+    }
+    // the sum is < 2^35 * q: P[8] and Qd[9] hold a few carries, the two reduction rows below add < 2^30 to limb 9
+    uint32_t m = fr_mont_m(P[0] + Qd[0]);
+    chain4(P[0], P[1], P[2], P[3], P[4], P[5], P[6], P[7], P[8], FR_Q0, FR_Q2, FR_Q4, FR_Q6, m);
+    chain4_cin(Qd[1], Qd[2], Qd[3], Qd[4], Qd[5], Qd[6], Qd[7], Qd[8], Qd[9], FR_Q1, FR_Q3, FR_Q5, FR_Q7, m, P[0], Qd[0]);
+    m = fr_mont_m(Qd[1] + P[1]);
+    chain4(Qd[1], Qd[2], Qd[3], Qd[4], Qd[5], Qd[6], Qd[7], Qd[8], Qd[9], FR_Q0, FR_Q2, FR_Q4, FR_Q6, m);
+    chain4_cin(P[2], P[3], P[4], P[5], P[6], P[7], P[8], P[9], P[10], FR_Q1, FR_Q3, FR_Q5, FR_Q7, m, Qd[1], P[1]);
+    (void)add8_carry(P + 2, Qd + 2);  // limbs 2..9 of P + Qd: the result, < 2q < 2^255
+    Fr v;
+#pragma unroll
+    for (int i = 0; i < 8; i++) v.v[i] = P[2 + i];
+    return fr_reduce_once(v);
+}
+
 // x^7 = ((x^2 * x)^2) * x  -- same chain as hash/poseidon.go:129-135 and circuit/gates/cipher.go:37-40
 __device__ __forceinline__ Fr fr_pow7(const Fr& x) {
     Fr t = fr_sqr(x);

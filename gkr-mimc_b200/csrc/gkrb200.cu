@@ -9,7 +9,9 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <linux/futex.h>
 #include <nccl.h>
+#include <sys/syscall.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -255,6 +257,7 @@ struct gkrb200_ctx {
                  const H::Fr* trusted_claim = nullptr);
     size_t par8_max_pairs = 8192;  // rounds with at most this many pairs spread one pair over 8 lanes
     size_t inline_min_pairs = 0;   // one-thread-per-pair rounds with at least this many pairs run the kernel with the inlined multiplier
+    bool const_fold = true;        // option: folds by the constant-multiplier product when the host knows the challenge at launch
     bool force_generic = false;  // test hook: run cipher layers through the generic evaluate-at-9-points kernel
     int exchange_and_fetch_wide(int nm, int wl, int W, uint32_t tag, H::Fr* out);
     int mle_eval(const FrRaw* table, int bn_total, const H::Fr* point, bool use_shards, H::Fr* out);
@@ -370,9 +373,15 @@ static inline size_t cf_smem_v(int nm, int variant) {  // variant: see CF_V_* be
 typedef void (*cf_kernel_t)(const gkr::RoundCfArgs);
 // variant: 0 = one thread per pair, multiplier inlined (big rounds); 1 = eight lanes per pair (small rounds);
 //          2 = one thread per pair, multiplier out of line (mid-size rounds / A-B reference)
-enum { CF_V_INL = 0, CF_V_PAR8 = 1, CF_V_CALL = 2 };
+//          3 = variant 0 with the folds done by the constant-multiplier product (the challenge is known to the host at launch)
+enum { CF_V_INL = 0, CF_V_PAR8 = 1, CF_V_CALL = 2, CF_V_INL_KFOLD = 3 };
 static cf_kernel_t cf_kernel(bool fold, int nm, int variant) {
     using namespace gkr;
+    if (variant == CF_V_INL_KFOLD) {
+        if (!fold) variant = CF_V_INL;
+        else return nm == 8 ? (cf_kernel_t)k_round_cf<true, 8, 1, CF_BLOCK_INL, CF_MINB_INL, true, true>
+                            : (cf_kernel_t)k_round_cf<true, 7, 1, CF_BLOCK_INL, CF_MINB_INL, true, true>;
+    }
 #define CF_K1(F, N) k_round_cf<F, N, 1, CF_BLOCK_INL, CF_MINB_INL, true>
 #define CF_K8(F, N) k_round_cf<F, N, 8, CF_BLOCK, CF_MINB8, false>
 #define CF_KC(F, N) k_round_cf<F, N, 1, CF_BLOCK1, CF_MINB1, false>
@@ -386,8 +395,8 @@ static cf_kernel_t cf_kernel(bool fold, int nm, int variant) {
 static int set_cf_attrs() {
     for (int f = 0; f < 2; f++)
         for (int n = 7; n <= 8; n++)
-            for (int v = 0; v < 3; v++)
-                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem_v(n, v)));
+            for (int v = 0; v < 4; v++)
+                CUDA_TRY(cudaFuncSetAttribute(cf_kernel(f, n, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cf_smem_v(n, v == CF_V_INL_KFOLD ? CF_V_INL : v)));
     return 0;
 }
 
@@ -428,9 +437,39 @@ static H::Fr wide_to_fr(const volatile uint64_t* w, int wl, int n_ranks, size_t 
     return H::add(H::add(H::mul(lo, H::Fr{{1, 0, 0, 0}}), mid), H::mul(H::Fr{{top, 0, 0, 0}}, R2));
 }
 
+// The constant-multiplier table of a fold challenge (fr_mul_const in fr_device.cuh): K_i = r * 2^(32i+64) * 2^-256 mod q.
+// H::mul is the Montgomery product x*y*2^-256, so K_i = H::mul(r, c_i) with c_i the plain integer 2^(32i+64) mod q.
+static gkr::FrConstMul const_mul_table(const H::Fr& r) {
+    static const struct Pows {
+        H::Fr c[8];
+        Pows() {
+            H::Fr v{{0, 1, 0, 0}};  // 2^64
+            for (int i = 0; i < 8; i++) {
+                c[i] = v;
+                for (int b = 0; b < 32; b++) v = H::dbl(v);  // * 2^32 mod q
+            }
+        }
+    } pw;
+    gkr::FrConstMul t;
+    for (int i = 0; i < 8; i++) {
+        const H::Fr k = H::mul(r, pw.c[i]);
+        for (int l = 0; l < 8; l++) t.k[i][l] = (uint32_t)(k.l[l >> 1] >> (32 * (l & 1)));
+    }
+    return t;
+}
+
 // ------------------------------------------------------------------------------------------------ init / free
-static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream);
-extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* stream) {
+static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream, int world);
+static size_t shard_cap(int max_bn, int world) {  // entries per table a rank of `world` holds (floor: see gkrb200_comm_init)
+    size_t want = (size_t)1 << max_bn;
+    int lw = 0;
+    while ((1 << lw) < world) lw++;
+    if (world > 1) want = std::max<size_t>(want >> lw, std::min<size_t>(want, 64));
+    return want;
+}
+extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* stream) { return gkrb200_init_shard(out, device, max_bn, stream, 1); }
+extern "C" int gkrb200_init_shard(gkrb200_ctx** out, int device, int max_bn, void* stream, int world) {
+    if (world < 1 || world > 8 || (world & (world - 1))) return fail(GKRB200_ERR_ARG, "bad world %d (a power of two <= 8)", world);
     if (!out || max_bn < 0 || max_bn > 26) return fail(GKRB200_ERR_ARG, "bad arguments to gkrb200_init (max_bn=%d)", max_bn);
     // the host transcript's multiplier is MULX/ADCX/ADOX assembly (fr_host.hpp): refuse to start on a CPU without them instead of SIGILL
     if (!__builtin_cpu_supports("adx") || !__builtin_cpu_supports("bmi2"))
@@ -442,7 +481,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     if (device < 0 || device >= ndev) return fail(GKRB200_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
     CUDA_TRY(cudaSetDevice(device));
     gkrb200_ctx* c = new gkrb200_ctx();
-    const int rc = init_ctx(c, device, max_bn, stream);
+    const int rc = init_ctx(c, device, max_bn, stream, world);
     if (rc) {
         gkrb200_free(c);  // releases whatever was built before the failure
         return rc;
@@ -450,7 +489,7 @@ extern "C" int gkrb200_init(gkrb200_ctx** out, int device, int max_bn, void* str
     *out = c;
     return 0;
 }
-static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
+static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream, int world) {
     c->device = device;
     c->max_bn = max_bn;
     cudaDeviceProp prop;
@@ -466,7 +505,7 @@ static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream) {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-    TRY(c->carve((size_t)1 << max_bn));
+    TRY(c->carve(shard_cap(max_bn, world)));
     CUDA_TRY(cudaMalloc(&c->ticket, 128));
     CUDA_TRY(cudaMemset(c->ticket, 0, 128));
     c->d_err = c->ticket + 16;
@@ -585,11 +624,7 @@ extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint
     while ((1 << c->log_world) < world) c->log_world++;
     // a sharded context holds 1/world of every table: shrink (or restore) the arena accordingly.  64 entries is the floor
     // (batches of at most `world` hashes run unsharded, and tiny sharded batches stage the full inputs).
-    {
-        size_t want = (size_t)1 << c->max_bn;
-        if (world > 1) want = std::max<size_t>(want >> c->log_world, std::min<size_t>(want, 64));
-        if (want != c->cap) TRY(c->carve(want));
-    }
+    if (shard_cap(c->max_bn, world) != c->cap) TRY(c->carve(shard_cap(c->max_bn, world)));
     if (world == 1) return 0;
     if (!g_nccl.load()) return fail(GKRB200_ERR_COMM, "cannot load libnccl.so.2 (or a symbol is missing)");
     ncclUniqueId id;
@@ -904,6 +939,7 @@ int gkrb200_ctx::residual_enqueue(const FrRaw* const* cur, int ntab, size_t lres
         f.half = lres;
         memcpy(&f.r, &r, 32);
         f.r_dev = r_dev;
+        if (!r_dev) f.rk = const_mul_table(r);
         LAUNCH(this, KC_FOLD, gkr::k_fold, 1, 128, 0, f);
     } else {
         for (int i = 0; i < ntab; i++)
@@ -970,19 +1006,24 @@ int gkrb200_ctx::post_header(int layer, const H::Fr* coeffs, size_t n_coeffs, co
     memcpy(h->fin, fin, (size_t)n_fin * sizeof(H::Fr));
     std::atomic_thread_fence(std::memory_order_release);
     h->seq = ++hseq;
+    // wake the followers sleeping on this header (a shared, non-private futex: the window is mapped by every rank's process)
+    syscall(SYS_futex, (uint32_t*)&h->seq, FUTEX_WAKE, 0x7fffffff, nullptr, nullptr, 0);
     return 0;
 }
-// Followers sleep here (they have nothing to compute): short naps instead of a spin, so a proof in flight costs ONE host core
+// Followers sleep here (they have nothing to compute) on a futex in the shared window, so a proof in flight costs ONE host core
 // (its leader's), not one per rank.
 int gkrb200_ctx::wait_header(int layer, H::Fr* coeffs, size_t n_coeffs, H::Fr* challenges, int bn_, H::Fr* fin, int n_fin) {
     LayerHeader* h = xheader(layer);
     const uint64_t want = ++hseq;
     const double t0 = now_ms();
     unsigned naps = 0;
-    while (h->seq != want) {
-        struct timespec ts = {0, 20000};  // 20 us
-        nanosleep(&ts, nullptr);
-        if ((++naps & 0x3ff) == 0) {
+    for (;;) {
+        const uint64_t have = h->seq;
+        if (have == want) break;
+        // sleep in the kernel until the leader posts (FUTEX_WAKE in post_header); the timeout only bounds the error checks below
+        struct timespec ts = {0, 2000000};  // 2 ms
+        syscall(SYS_futex, (uint32_t*)&h->seq, FUTEX_WAIT, (uint32_t)have, &ts, nullptr, 0);
+        if ((++naps & 0x3f) == 0) {
             cudaError_t q = cudaStreamQuery(stream);
             if (q != cudaSuccess && q != cudaErrorNotReady) return fail(GKRB200_ERR_CUDA, "stream error while waiting for the leader: %s", cudaGetErrorString(q));
             if (now_ms() - t0 > 60000.0) return fail(GKRB200_ERR_COMM, "timeout waiting for the leader's header of layer %d (have %llu, want %llu)", layer,
@@ -1274,12 +1315,17 @@ int gkrb200_ctx::sumcheck_cf(const FrRaw* x0, const FrRaw* x1, int bn, const H::
         a.red.result = windowed(W) ? (unsigned long long*)xslot_d(tag, rank) : (W > 1 ? (unsigned long long*)d_local : (unsigned long long*)h_result);
         a.red.seq = tag;
         a.red.chal = lead ? chal_wait(tag, k) : gkr::ChalWait{nullptr, nullptr, nullptr, 0};
-        const int variant = par8 ? CF_V_PAR8 : (half >= inline_min_pairs ? CF_V_INL : CF_V_CALL);
-        const int blk = par8 ? CF_BLOCK : (variant == CF_V_INL ? CF_BLOCK_INL : CF_BLOCK1);
-        int bps1 = variant == CF_V_INL ? cf_blocks_per_sm_inl[nm - 7] : cf_blocks_per_sm1[nm - 7];
+        int variant = par8 ? CF_V_PAR8 : (half >= inline_min_pairs ? CF_V_INL : CF_V_CALL);
+        const bool inl = variant == CF_V_INL;
+        if (inl && do_fold && !a.r_dev && const_fold) {  // the host knows r: fold by the constant-multiplier product
+            a.rk = const_mul_table(r);
+            variant = CF_V_INL_KFOLD;
+        }
+        const int blk = par8 ? CF_BLOCK : (inl ? CF_BLOCK_INL : CF_BLOCK1);
+        int bps1 = inl ? cf_blocks_per_sm_inl[nm - 7] : cf_blocks_per_sm1[nm - 7];
         if (cf_blocks_cap > 0 && bps1 > cf_blocks_cap) bps1 = cf_blocks_cap;
         const int grid = grid_for(par8 ? half * 8 : half, blk, n_sm * (par8 ? CF_MINB8 : bps1));  // at most one resident wave
-        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, variant), grid, blk, cf_smem_v(nm, variant), a);
+        LAUNCH(this, KC_ROUND, cf_kernel(do_fold, nm, variant), grid, blk, cf_smem_v(nm, inl ? CF_V_INL : variant), a);
         CUDA_TRY(cudaGetLastError());
         // algorithmic multiplier work in units of one Montgomery product (136 wide multiply-adds): 9 (NM = 8: 11) full products,
         // NM plain 512-bit products of 64 multiply-adds each, the eq factor product and four folds
@@ -1520,6 +1566,7 @@ int gkrb200_ctx::mle_eval(const FrRaw* table, int bn, const H::Fr* point, bool u
         f.dst[0] = dst;
         f.half = len / 2;
         memcpy(&f.r, &point[k], 32);
+        f.rk = const_mul_table(point[k]);
         LAUNCH(this, KC_FOLD, gkr::k_fold, grid_for(f.half, 256, n_sm * 8), 256, 0, f);
         cur = dst;
         len /= 2;
@@ -1736,6 +1783,11 @@ extern "C" int gkrb200_fold(gkrb200_ctx* c, const uint64_t* table, size_t n, con
         f.dst[0] = d + n;
         f.half = n / 2;
         memcpy(&f.r, r, 32);
+        {
+            H::Fr rr;
+            memcpy(&rr, r, 32);
+            f.rk = const_mul_table(rr);
+        }
         LAUNCH(c, KC_FOLD, gkr::k_fold, grid_for(n / 2, 256, c->n_sm * 8), 256, 0, f);
         cudaError_t e = cudaMemcpyAsync(out, d + n, (n / 2) * sizeof(FrRaw), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1937,6 +1989,10 @@ extern "C" int gkrb200_set_option(gkrb200_ctx* c, int option, long value) {
         case GKRB200_OPT_INLINE_MIN_PAIRS:
             if (value < 0) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
             c->inline_min_pairs = (size_t)value;
+            return 0;
+        case GKRB200_OPT_CONST_FOLD:
+            if (value != 0 && value != 1) return fail(GKRB200_ERR_ARG, "bad value %ld", value);
+            c->const_fold = value == 1;
             return 0;
         case GKRB200_OPT_TRANSCRIPT:
             if (value != 0 && value != 1) return fail(GKRB200_ERR_ARG, "bad value %ld", value);

@@ -207,6 +207,7 @@ struct FoldArgs {
     size_t half;
     FrRaw r;
     const FrRaw* r_dev;  // when not null: the challenge is read from device memory instead of a.r
+    FrConstMul rk;       // r_dev == nullptr: the constant-multiplier table of r (fr_mul_const)
 };
 __global__ void __launch_bounds__(256) k_fold(const FoldArgs a) {
     const Fr r = a.r_dev ? fr_load(a.r_dev) : fr_unpack(a.r);
@@ -226,8 +227,13 @@ __global__ void __launch_bounds__(256) k_fold(const FoldArgs a) {
         FrRaw* d2 = t2 == 0 ? a.dst[0] : (t2 == 1 ? a.dst[1] : a.dst[2]);
         const Fr b = fr_load_stream(s1 + x), u = fr_load_stream(s1 + x + a.half);
         const Fr b2 = fr_load_stream(s2 + x2), u2 = fr_load_stream(s2 + x2 + a.half);
-        fr_store(d1 + x, fr_add(b, fr_mul(r, fr_sub(u, b))));
-        if (two) fr_store(d2 + x2, fr_add(b2, fr_mul(r, fr_sub(u2, b2))));
+        if (a.r_dev) {
+            fr_store(d1 + x, fr_add(b, fr_mul(r, fr_sub(u, b))));
+            if (two) fr_store(d2 + x2, fr_add(b2, fr_mul(r, fr_sub(u2, b2))));
+        } else {
+            fr_store(d1 + x, fr_add(b, fr_mul_const(a.rk, fr_sub(u, b))));
+            if (two) fr_store(d2 + x2, fr_add(b2, fr_mul_const(a.rk, fr_sub(u2, b2))));
+        }
     }
 }
 
@@ -695,6 +701,7 @@ struct RoundCfArgs {
     size_t half;          // number of pairs x'
     FrRaw r;              // previous challenge (FOLD) ...
     const FrRaw* r_dev;   // ... or, when not null, where the previous launch's last block left it in device memory
+    FrConstMul rk;        // KFOLD kernels: the constant-multiplier table of r (80 instead of 136 wide multiply-adds per fold)
     FrRaw ark;            // CipherGate.Ark
     const FrRaw* tA;      // high suffix table of this round or nullptr
     const FrRaw* tB;      // low table (2^c entries when tA != nullptr, else `half` entries)
@@ -747,7 +754,7 @@ __device__ __forceinline__ void cf_acc(uint32_t* sm, int tid, int block, unsigne
     }
 }
 
-template <bool FOLD, int NM, int PAR, int BLOCK, int MINB, bool INL>
+template <bool FOLD, int NM, int PAR, int BLOCK, int MINB, bool INL, bool KFOLD = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
     static_assert(NM == 7 || NM == 8, "7 coefficient sums (m_7 from the claim) or all 8");
     static_assert(PAR == 1 || PAR == 8, "one thread or eight lanes per pair");
@@ -783,13 +790,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
                 const Fr l1 = fr_load_stream(a.src[0] + x + half), h1 = fr_load_stream(a.src[0] + x + half + m2);
                 const Fr l2 = fr_load_stream(a.src[1] + x), h2 = fr_load_stream(a.src[1] + x + m2);
                 const Fr l3 = fr_load_stream(a.src[1] + x + half), h3 = fr_load_stream(a.src[1] + x + half + m2);
-                const Fr b0 = fr_add(l0, cf_mul<INL>(r, fr_sub(h0, l0)));
+                const Fr b0 = fr_add(l0, KFOLD ? fr_mul_const(a.rk, fr_sub(h0, l0)) : cf_mul<INL>(r, fr_sub(h0, l0)));
                 fr_store(a.dst[0] + x, b0);
-                const Fr t0 = fr_add(l1, cf_mul<INL>(r, fr_sub(h1, l1)));
+                const Fr t0 = fr_add(l1, KFOLD ? fr_mul_const(a.rk, fr_sub(h1, l1)) : cf_mul<INL>(r, fr_sub(h1, l1)));
                 fr_store(a.dst[0] + x + half, t0);
-                const Fr b1 = fr_add(l2, cf_mul<INL>(r, fr_sub(h2, l2)));
+                const Fr b1 = fr_add(l2, KFOLD ? fr_mul_const(a.rk, fr_sub(h2, l2)) : cf_mul<INL>(r, fr_sub(h2, l2)));
                 fr_store(a.dst[1] + x, b1);
-                const Fr t1 = fr_add(l3, cf_mul<INL>(r, fr_sub(h3, l3)));
+                const Fr t1 = fr_add(l3, KFOLD ? fr_mul_const(a.rk, fr_sub(h3, l3)) : cf_mul<INL>(r, fr_sub(h3, l3)));
                 fr_store(a.dst[1] + x + half, t1);
                 av = fr_add(fr_add(b0, b1), ark);                 // cipher.go:34-35 on the bottom half
                 bv = fr_add(fr_sub(t0, b0), fr_sub(t1, b1));      // (top + ark) - (bottom + ark)

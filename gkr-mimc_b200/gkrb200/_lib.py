@@ -50,6 +50,7 @@ def lib():
     L.gkrb200_last_error.restype = ctypes.c_char_p
     L.gkrb200_version.restype = ctypes.c_char_p
     L.gkrb200_init.argtypes = [ctypes.POINTER(vp), i32, i32, vp]
+    L.gkrb200_init_shard.argtypes = [ctypes.POINTER(vp), i32, i32, vp, i32]
     L.gkrb200_free.argtypes = [vp]
     L.gkrb200_free.restype = None
     L.gkrb200_comm_unique_id.argtypes = [vp]

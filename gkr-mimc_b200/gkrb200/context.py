@@ -23,9 +23,10 @@ def fr_empty(*shape):
 
 
 class Context:
-    def __init__(self, device=0, max_bn=16, stream=None):
+    def __init__(self, device=0, max_bn=16, stream=None, world=1):
+        """world > 1: the context will join a communicator of that many ranks; its arena is sized for the 1/world shard"""
         self._h = ctypes.c_void_p()
-        check(lib().gkrb200_init(ctypes.byref(self._h), device, max_bn, ctypes.c_void_p(stream) if stream else None))
+        check(lib().gkrb200_init_shard(ctypes.byref(self._h), device, max_bn, ctypes.c_void_p(stream) if stream else None, world))
         self.device, self.max_bn = device, max_bn
         self.rank, self.world = 0, 1
 
@@ -77,7 +78,7 @@ class Context:
     def set_profiling(self, on):
         check(lib().gkrb200_set_profiling(self._h, 1 if on else 0))
 
-    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN, OPT_CF_BLOCKS_PER_SM, OPT_EXCHANGE, OPT_INLINE_MIN_PAIRS, OPT_TRANSCRIPT = 1, 2, 3, 4, 5, 6, 7
+    OPT_GENERIC_CIPHER, OPT_PAR8_MAX_PAIRS, OPT_HOST_TAIL_LEN, OPT_CF_BLOCKS_PER_SM, OPT_EXCHANGE, OPT_INLINE_MIN_PAIRS, OPT_TRANSCRIPT, OPT_CONST_FOLD = 1, 2, 3, 4, 5, 6, 7, 8
 
     def set_option(self, option, value):
         check(lib().gkrb200_set_option(self._h, option, int(value)))

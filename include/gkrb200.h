@@ -53,6 +53,10 @@ const char *gkrb200_version(void);
  * sumcheck/worker.go:8-26: one device arena sized for batches up to 2^max_bn, one stream, pinned result slots.
  * `stream` may be NULL (the library creates one) or a cudaStream_t owned by the caller.               */
 int gkrb200_init(gkrb200_ctx **ctx, int device, int max_bn, void *stream);
+/* Same for a context that will join a communicator of `world` ranks (gkrb200_comm_init): the arena is sized for this rank's
+ * 1/world shard from the start (93 x 2^max_bn / world entries) instead of being shrunk at comm_init -- what lets many contexts
+ * (proofs in flight) be created side by side on one GPU.                                                                   */
+int gkrb200_init_shard(gkrb200_ctx **ctx, int device, int max_bn, void *stream, int world);
 void gkrb200_free(gkrb200_ctx *ctx);
 
 /* Multi-GPU: one context per process/GPU.  Rank r of `world` (a power of two <= 8) owns the entries
@@ -224,6 +228,10 @@ int gkrb200_set_profiling(gkrb200_ctx *ctx, int on);
  * by device-side waits, follower ranks only enqueue kernels and sleep; 1 = every rank runs the transcript itself, in lockstep
  * (round-1 behaviour, A/B reference; implied when the exchange is NCCL).                                                   */
 #define GKRB200_OPT_TRANSCRIPT 7
+/* GKRB200_OPT_CONST_FOLD (default 1): fold with the constant-multiplier product (80 instead of 136 wide multiply-adds; the host
+ * derives a small table from the challenge at launch) wherever the challenge is known to the host; 0 = plain Montgomery
+ * products (A/B reference: both give identical bytes).                                                                     */
+#define GKRB200_OPT_CONST_FOLD 8
 int gkrb200_set_option(gkrb200_ctx *ctx, int option, long value);
 
 /* integer-pipe microbenchmarks for the roofline denominator: returns achieved rate.
