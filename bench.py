@@ -29,6 +29,11 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "gkr-mimc_b200"))
+# Every proof in flight owns a stream on which a whole layer of launches is pre-enqueued, each waiting on the previous one.  With the
+# driver's default of 8 hardware work queues several streams share a queue, and a launch that is waiting for its predecessor holds
+# back the independent launches of another proof queued behind it (false dependency).  32 queues = one per stream.  Must be set
+# before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 _JSON_OUT = sys.stdout
 METRIC = "proven MiMC hashes/sec (bit-exact GKR proof)"
@@ -309,14 +314,17 @@ def main():
     elif replicas:
         P = max(1, min(8, args.steps, cores // world))
     elif sharded:
-        # one spinning/hashing host thread per proof in flight on the whole box (its leader); the other ranks' threads sleep on a futex
-        P = max(1, min(max(8, 3 * world), args.steps, cores - max(2, cores // 4)))
+        # one spinning/hashing host thread per proof in flight on the whole box (its leader); the other ranks' threads sleep.
+        # 8 in flight is the configuration validated on 2 and 8 x B200 (profiles/r2_bench_bn22_n{2,8}_leader*.json); a first attempt
+        # with 24 in flight on 8 GPUs did not finish (profiles/r2_note_p24_n8.txt), so more is opt-in (--inflight).
+        P = max(1, min(8, args.steps, cores - 2))
     else:
         P = max(1, min(8, args.steps, cores - 2))
     main_stream = torch.cuda.Stream()
     streams = [torch.cuda.Stream() for _ in range(P)]  # the library launches on these; events are recorded on main_stream after joining them
     torch.cuda.set_stream(main_stream)
-    ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream, world=world if sharded else 1) for st_ in streams]
+    # more than 8 sharded contexts per GPU only fit when their arenas are sized for the shard from the start (gkrb200_init_shard)
+    ctxs = [gkrb200.Context(device=local_rank, max_bn=bn, stream=st_.cuda_stream, world=world if (sharded and P > 8) else 1) for st_ in streams]
     ctx = ctxs[0]
     if sharded:
         for i, c in enumerate(ctxs):  # one communicator per pipeline, created in the same order on every rank

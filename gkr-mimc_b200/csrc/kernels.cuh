@@ -720,6 +720,12 @@ __device__ __forceinline__ Fr load_fold_one(const FrRaw* src, FrRaw* dst, size_t
     return fr_load_stream(src + idx);
 }
 
+#ifndef GKR_ACC_LOOP
+#define GKR_ACC_LOOP 0
+#endif
+#ifndef GKR_CUBIC_LOOP
+#define GKR_CUBIC_LOOP 0
+#endif
 // INL: the multiplier is inlined at every call site (big rounds: no call ABI, no IMAD.MOV marshalling on the multiplier's
 // pipe) or called out of line (small rounds: short cold instruction fetch)
 template <bool INL>
@@ -811,6 +817,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
             // T a, T a^4 and T a b^3 (3 products) give all of m_0..m_6 as products that only feed the sums, and those are
             // accumulated UNREDUCED (fr_mul_acc_wide).  9 Montgomery products per pair instead of 11 for powers + chain.
             Fr v30, v21, v12, v03;
+#if GKR_CUBIC_LOOP
+            if (INL) {
+                // (x, y) = (a, b) then (b, a): x^2, x^2 x, x^2 y -- one rolled body instead of two copies (~9 KB of code); the
+                // results rotate through (v30, v21) <- (v03, v12) <- (x^3, x^2 y), so after two turns v30 = a^3, v21 = a^2 b, v03 = b^3, v12 = b^2 a
+                Fr x = av, y = bv;
+#pragma unroll 1
+                for (int k = 0; k < 2; k++) {
+                    const Fr x2 = fr_sqr(x);
+                    v30 = v03;
+                    v21 = v12;
+                    v03 = fr_mul(x2, x);
+                    v12 = fr_mul(x2, y);
+                    const Fr t = x;
+                    x = y;
+                    y = t;
+                }
+            } else
+#endif
             {
                 const Fr a2 = cf_sqr<INL>(av), b2 = cf_sqr<INL>(bv);
                 v30 = cf_mul<INL>(a2, av);
@@ -823,17 +847,48 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_round_cf(const RoundCfArgs a) {
                 cf_acc<INL, 7>(sm, tid, BLOCK, ovf, tb4, v03);
             }
             u = cf_mul<INL>(u, av);  // T a
-            {
+#if GKR_ACC_LOOP
+            if (INL) {
+                // The seven plain products as ONE rolled loop body (operands picked with selects on the ALU pipe, which has the
+                // headroom): 6 copies fewer of a ~140-instruction body, i.e. ~13 KB less for the instruction cache to stream.
                 const Fr u1 = cf_mul<INL>(u, v03);  // T a b^3
-                cf_acc<INL, 4>(sm, tid, BLOCK, ovf, u1, v21);
-                cf_acc<INL, 5>(sm, tid, BLOCK, ovf, u1, v12);
-                cf_acc<INL, 6>(sm, tid, BLOCK, ovf, u1, v03);
+                u = cf_mul<INL>(u, v30);            // T a^4
+#pragma unroll 1
+                for (int k = 0; k < 7; k++) {
+                    const int ri = k < 4 ? k : k - 3;  // m_0..m_3 = T a^4 * {a^3, a^2 b, a b^2, b^3};  m_4..m_6 = T a b^3 * {a^2 b, a b^2, b^3}
+                    Fr lf, rf;
+#pragma unroll
+                    for (int l = 0; l < 8; l++) {
+                        lf.v[l] = k < 4 ? u.v[l] : u1.v[l];
+                        rf.v[l] = ri == 0 ? v30.v[l] : (ri == 1 ? v21.v[l] : (ri == 2 ? v12.v[l] : v03.v[l]));
+                    }
+                    uint32_t* acc = sm + (size_t)k * 16 * BLOCK + tid;
+                    uint32_t p[16];
+                    fr_mul_wide(p, lf, rf);
+                    uint32_t w[16];
+#pragma unroll
+                    for (int l = 0; l < 16; l++) w[l] = acc[l * BLOCK];
+                    uint32_t c = add8_carry(w, p);
+                    c = add8_carry_in(w + 8, p + 8, c);
+                    ovf += (unsigned long long)c << (8 * k);
+#pragma unroll
+                    for (int l = 0; l < 16; l++) acc[l * BLOCK] = w[l];
+                }
+            } else
+#endif
+            {
+                {
+                    const Fr u1 = cf_mul<INL>(u, v03);  // T a b^3
+                    cf_acc<INL, 4>(sm, tid, BLOCK, ovf, u1, v21);
+                    cf_acc<INL, 5>(sm, tid, BLOCK, ovf, u1, v12);
+                    cf_acc<INL, 6>(sm, tid, BLOCK, ovf, u1, v03);
+                }
+                u = cf_mul<INL>(u, v30);  // T a^4
+                cf_acc<INL, 3>(sm, tid, BLOCK, ovf, u, v03);
+                cf_acc<INL, 2>(sm, tid, BLOCK, ovf, u, v12);
+                cf_acc<INL, 1>(sm, tid, BLOCK, ovf, u, v21);
+                cf_acc<INL, 0>(sm, tid, BLOCK, ovf, u, v30);
             }
-            u = cf_mul<INL>(u, v30);  // T a^4
-            cf_acc<INL, 3>(sm, tid, BLOCK, ovf, u, v03);
-            cf_acc<INL, 2>(sm, tid, BLOCK, ovf, u, v12);
-            cf_acc<INL, 1>(sm, tid, BLOCK, ovf, u, v21);
-            cf_acc<INL, 0>(sm, tid, BLOCK, ovf, u, v30);
         }
     } else {
         const int j = tid & 7;

@@ -3,6 +3,7 @@ byte-identical proof vector on every rank, equal to the oracle's, for every batc
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gkr-mimc_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np
 import torch
 import torch.distributed as dist
