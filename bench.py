@@ -32,8 +32,9 @@ sys.path.insert(0, os.path.join(ROOT, "gkr-mimc_b200"))
 # Every proof in flight owns a stream on which a whole layer of launches is pre-enqueued, each waiting on the previous one.  With the
 # driver's default of 8 hardware work queues several streams share a queue, and a launch that is waiting for its predecessor holds
 # back the independent launches of another proof queued behind it (false dependency).  32 queues = one per stream.  Must be set
-# before CUDA initialises.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# before CUDA initialises.  Single-GPU runs launch one round at a time and keep the driver's default.
+if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 _JSON_OUT = sys.stdout
 METRIC = "proven MiMC hashes/sec (bit-exact GKR proof)"
