@@ -1,11 +1,14 @@
 // Device kernels of the GKR-MiMC prover (sm_100a).  One kernel per CPU hot loop of the reference:
 //   K1 k_mimc_assign   <- Circuit.Assign / Layer.Evaluate / CipherGate.EvalBatch   (circuit/assignment.go:12-32,
 //                         circuit/circuit.go:48-64, circuit/gates/cipher.go:25-42)
-//   K2 k_eq_small + k_eq_expand <- poly.FoldedEqTable / ChunkOfEqTable             (poly/eq.go:41-89)
+//   K2 k_eq_suffix / k_eq_small + k_eq_expand <- poly.FoldedEqTable / ChunkOfEqTable (poly/eq.go:41-89)
 //   K5 k_eq_expand (n_claims>1) <- multi-claim combination                         (sumcheck/prover.go:121-141, algo.go:219-223)
-//   K3 k_round (eval)  <- getPartialPolyChunk + consumeAccumulate                  (sumcheck/algo.go:54-205, prover.go:236-245)
-//   K4 k_round (fold) / k_fold <- MultiLin.FoldChunk                               (poly/multilin.go:26-36, sumcheck/algo.go:46-51)
-// All tables are arrays of FrRaw (Go's fr.Element image), moved with 256-bit accesses.
+//   K3 k_round_cf (factored cipher round) / k_round (generic) <- getPartialPolyChunk + consumeAccumulate
+//                                                                                  (sumcheck/algo.go:54-205, prover.go:236-245)
+//   K4 fold fused into the round kernels / k_fold <- MultiLin.FoldChunk            (poly/multilin.go:26-36, sumcheck/algo.go:46-51)
+//   staging: k_destripe, k_take_shard (multi-GPU input shards), k_convert, k_hash_out (hint I/O, prover/gadget/hints.go:197-233)
+// All tables are arrays of FrRaw (Go's fr.Element image), moved with 256-bit accesses.  Results leave the device as tagged 64-bit
+// words (publish_word); the verifier challenge can come back the same way (ChalWait).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -24,11 +27,6 @@ __constant__ FrRaw c_arks[91] = {
 // Shared layout u32 sm[NACC][8][BLOCK] (thread index fastest => conflict-free).  Field addition is
 // exact, so the summation order is irrelevant to the result (no determinism concern).
 // ------------------------------------------------------------------------------------------------
-template <int NACC, int BLOCK>
-__device__ __forceinline__ void smem_put(uint32_t* sm, int k, int tid, const Fr& a) {
-#pragma unroll
-    for (int l = 0; l < 8; l++) sm[(k * 8 + l) * BLOCK + tid] = a.v[l];
-}
 template <int BLOCK>
 __device__ __forceinline__ Fr smem_get(const uint32_t* sm, int k, int tid) {
     Fr a;
@@ -708,17 +706,6 @@ struct RoundCfArgs {
     int c;
     WideOut red;
 };
-
-template <bool FOLD>
-__device__ __forceinline__ Fr load_fold_one(const FrRaw* src, FrRaw* dst, size_t idx, size_t stride2, const Fr& r) {
-    if (FOLD) {
-        const Fr lo = fr_load_stream(src + idx), hi = fr_load_stream(src + idx + stride2);
-        const Fr f = fr_add(lo, fr_mulc(r, fr_sub(hi, lo)));
-        fr_store(dst + idx, f);
-        return f;
-    }
-    return fr_load_stream(src + idx);
-}
 
 #ifndef GKR_ACC_LOOP
 #define GKR_ACC_LOOP 0
