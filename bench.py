@@ -436,11 +436,17 @@ def main():
     out_sha_local = sha(out_hn[0])
 
     # roofline pass: one extra step with CUDA events around every kernel launch (on the launching stream)
+    # (sharded: in lockstep mode for this one step -- in leader mode a round kernel's last block stays resident until the challenge
+    # derived from its sums arrives, so launch-to-completion times would include the host transcript)
+    if sharded and ctx.exchange_mode == "window":
+        ctx.set_option(gkrb200.Context.OPT_TRANSCRIPT, 1)
     ctx.set_profiling(True)
     ctx.stats_reset()
     step_resident()
     sp = ctx.stats()
     ctx.set_profiling(False)
+    if sharded and ctx.exchange_mode == "window" and "7=1" not in args.opt:
+        ctx.set_option(gkrb200.Context.OPT_TRANSCRIPT, 0)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
