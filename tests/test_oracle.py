@@ -223,6 +223,27 @@ def test_circuit_structure(oracle):
         assert oracle.from_mont(lay[l]) == a[l]
 
 
+def test_c_oracle_worker_pool_has_no_stale_ticket_race(oracle):
+    """Regression: the worker pool once validated a ticket drawn in an earlier run against the NEXT run's task count, so under
+    preemption a task ran twice and the caller went on one task early -- ~3 % of the 91-claim eq tables (181 back-to-back tiny
+    pool runs, sumcheck/prover.go:121-141) came out wrong at bn = 11.  200 oversubscribed repetitions catch that with
+    probability > 0.99; the oracle is the checker of every GPU parity test, so it must be exactly reproducible."""
+    bn, nq = 11, 91
+    qp = oracle.random_fr_array(nq * bn + 7)[7:].reshape(nq, bn, 4)
+    cl = oracle.random_fr_array(nq + 3)[3:]
+    oracle.set_threads(1)
+    ref_eq, ref_rho = oracle.make_eq_table(cl, qp)
+    try:
+        for threads in (8, 32):
+            oracle.set_threads(threads)
+            for _ in range(100):
+                eq, rho = oracle.make_eq_table(cl, qp)
+                assert np.array_equal(rho, ref_rho)
+                assert np.array_equal(eq, ref_eq), "the multi-threaded eq table differs from the single-threaded one"
+    finally:
+        oracle.set_threads(min(8, os.cpu_count() or 1))
+
+
 def test_c_oracle_thread_count_invariance(oracle):
     """the worker-pool decomposition (common/parallelize.go, sumcheck/worker.go) must not change any word"""
     bn = 11
