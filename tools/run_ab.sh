@@ -6,14 +6,14 @@ python - <<'PY' > gpurun_out/ab_micro.txt 2>&1
 import sys; sys.path.insert(0, "gkr-mimc_b200")
 import gkrb200
 ctx = gkrb200.Context(0, 10)
-for kind, name in ((4, "schoolbook fr_mul"), (5, "Karatsuba fr_mul")):
+for kind, name in ((1, "inlined fr_mul"), (4, "out-of-line fr_mulc")):
     print("%-20s full occupancy: %.1f G/s" % (name, ctx.microbench(kind, 1000)[0]))
     for w in (8, 12, 16):
         print("%-20s %2d warps/SM   : %.1f G/s" % (name, w, ctx.microbench(kind | (w << 8), 1000)[0]))
 ctx.close()
 PY
 cat gpurun_out/ab_micro.txt
-for V in "" mixed school; do
+for V in ""; do  # round 1 compared the kara / mixed builds here (tools/exp/fr_kara.cuh); make variant NAME=.. DEFS=.. builds others
   export GKRB200_LIB_VARIANT=$V
   T=${V:-kara}
   ( timeout 600 python -m pytest tests -m gpu -x -q ) > gpurun_out/ab_pytest_$T.log 2>&1; echo "pytest[$T] rc=$?"; tail -2 gpurun_out/ab_pytest_$T.log
