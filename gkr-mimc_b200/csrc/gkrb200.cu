@@ -458,6 +458,16 @@ static gkr::FrConstMul const_mul_table(const H::Fr& r) {
     return t;
 }
 
+// test hook: the table the fold kernels receive for a challenge r (64 words: K_0..K_7, 8 x 32-bit limbs each, low limb first)
+extern "C" int gkrb200_const_mul_table(const uint64_t* r, uint32_t* out64) {
+    if (!r || !out64) return fail(GKRB200_ERR_ARG, "null argument");
+    H::Fr rr;
+    memcpy(&rr, r, 32);
+    const gkr::FrConstMul t = const_mul_table(rr);
+    memcpy(out64, t.k, sizeof t.k);
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ init / free
 static int init_ctx(gkrb200_ctx* c, int device, int max_bn, void* stream, int world);
 static size_t shard_cap(int max_bn, int world) {  // entries per table a rank of `world` holds (floor: see gkrb200_comm_init)

@@ -75,6 +75,7 @@ def lib():
     L.gkrb200_to_montgomery.argtypes = [vp, sz, vp]
     L.gkrb200_from_montgomery.argtypes = [vp, sz, vp]
     L.gkrb200_mimc_ark.argtypes = [i32, vp]
+    L.gkrb200_const_mul_table.argtypes = [vp, vp]
     L.gkrb200_eval_univariate.argtypes = [vp, sz, vp, vp]
     L.gkrb200_eval_eq.argtypes = [vp, vp, sz, vp]
     L.gkrb200_fr_scalar.argtypes = [i32, vp, vp, vp]

@@ -166,6 +166,9 @@ int gkrb200_interpolate(const uint64_t *evals, size_t n, uint64_t *coeffs_out);
 int gkrb200_to_montgomery(const uint64_t *in, size_t n, uint64_t *out);
 int gkrb200_from_montgomery(const uint64_t *in, size_t n, uint64_t *out);
 
+/* test hook for the constant-multiplier fold: the 8 residues K_i = r * 2^(32i+64) * 2^-256 mod q the fold
+ * kernels receive for a challenge r (Montgomery image of r in, 8 x 8 32-bit limbs out, low limb first); host-only.            */
+int gkrb200_const_mul_table(const uint64_t *r, uint32_t *out64);
 /* hash.Arks[round], round 0..90 (hash/ark.go:13-337): the constant of the cipher gate of layer round+3 (examples/mimc.go:29) */
 int gkrb200_mimc_ark(int round, uint64_t *out);
 /* poly.EvalUnivariate (poly/lagrange.go:31-39): coefficients low -> high, n >= 1                            */

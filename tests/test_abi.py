@@ -220,3 +220,56 @@ def test_check_mimc_circuit_accepts_only_the_mimc_wiring():
         c.check(arks)
     assert "layer 40" in str(e.value) and "Ark" in str(e.value)
     assert gkrb200.lib().gkrb200_check_mimc_circuit(94, None, None, None, None) == -1
+
+
+def test_const_mul_table_and_the_fold_product_it_drives(oracle):
+    """Host side of the constant-multiplier fold (fr_mul_const, csrc/fr_device.cuh): K_i = r * 2^(32i+64) * 2^-256 mod q, and the
+    device algorithm restated limb for limb on those K_i -- 64 products sum_i d_i * K_i with every row at limb 0, then two
+    Montgomery rows -- yields fr.Element.Mul(r, d) for edge and random operands (the GPU parity tests check the kernel itself)."""
+    import random
+    import gkrb200
+    Q = oracle.Q
+    R = 1 << 256
+    rinv = pow(R, -1, Q)
+    M32 = 0xFFFFFFFF
+    qinv32 = (-pow(Q, -1, 1 << 32)) % (1 << 32)
+    ql = [(Q >> (32 * i)) & M32 for i in range(8)]
+    rnd = random.Random(11)
+
+    def enc(v):
+        return np.array([(v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)], dtype=np.uint64)
+
+    def chain(acc, start, xs, y, cin=0):
+        carry = cin
+        for k, x in enumerate(xs):
+            p = x * y
+            i = start + 2 * k
+            t = acc[i] + (p & M32) + carry
+            acc[i], carry = t & M32, t >> 32
+            t = acc[i + 1] + (p >> 32) + carry
+            acc[i + 1], carry = t & M32, t >> 32
+        acc[start + 2 * len(xs)] += carry
+        assert acc[start + 2 * len(xs)] <= M32  # the limb a chain carries out into never wraps
+
+    vals = [0, 1, Q - 1, Q - 2, Q // 2, (1 << 253) - 1, R % Q] + [rnd.randrange(Q) for _ in range(40)]
+    for r in vals[:12] + vals[-8:]:
+        out = np.zeros(64, dtype=np.uint32)
+        assert gkrb200.lib().gkrb200_const_mul_table(enc(r).ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == 0
+        K = out.reshape(8, 8).tolist()
+        for i in range(8):
+            assert sum(K[i][l] << (32 * l) for l in range(8)) == r * pow(2, 32 * i + 64, Q) * rinv % Q
+        for d in vals:
+            dl = [(d >> (32 * i)) & M32 for i in range(8)]
+            P, Qd = [0] * 12, [0] * 12
+            for i in range(8):
+                chain(P, 0, K[i][0::2], dl[i])
+                chain(Qd, 1, K[i][1::2], dl[i])
+            m = ((P[0] + Qd[0]) * qinv32) & M32
+            chain(P, 0, ql[0::2], m)
+            chain(Qd, 1, ql[1::2], m, cin=(P[0] + Qd[0]) >> 32)
+            m = ((Qd[1] + P[1]) * qinv32) & M32
+            chain(Qd, 1, ql[0::2], m)
+            chain(P, 2, ql[1::2], m, cin=(Qd[1] + P[1]) >> 32)
+            u = sum((P[i] + Qd[i]) << (32 * (i - 2)) for i in range(2, 12))
+            assert u < 2 * Q
+            assert (u - Q if u >= Q else u) == r * d * rinv % Q
