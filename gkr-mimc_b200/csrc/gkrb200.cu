@@ -705,6 +705,18 @@ extern "C" int gkrb200_comm_init(gkrb200_ctx* c, int rank, int world, const uint
     c->use_window = all_ok;
     c->xseq = 0;
     c->hseq = 0;
+    // Leader mode pre-enqueues a whole layer of mutually waiting launches per context.  If several contexts' streams share one
+    // hardware work queue, a waiting launch of one proof can hold back a ready launch of another whose sums the first proof's
+    // leader (through another rank) is waiting for.  One queue per stream avoids that; say so once if the process did not ask for it.
+    if (all_ok) {
+        static std::once_flag warned;
+        const char* mc = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+        if (!mc || atoi(mc) < 16)
+            std::call_once(warned, [] {
+                fprintf(stderr, "gkrb200: note: with several proofs in flight per GPU set CUDA_DEVICE_MAX_CONNECTIONS=32 before CUDA "
+                                "initialises (one hardware work queue per stream; see INTEGRATION.md section 5)\n");
+            });
+    }
     if (!all_ok && getenv("GKRB200_VERBOSE")) fprintf(stderr, "gkrb200: rank %d: no shared exchange window (ok=%d), using NCCL all-gather\n", rank, (int)ok);
     return 0;
 }
