@@ -14,6 +14,14 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _free_port():
+    """a TCP port the kernel just handed out as free (avoids collisions between consecutive rendezvous on a fixed port)"""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _to_t(vals):
     """field elements as 5 x 62-bit limbs in an int64 tensor (gloo has no 256-bit dtype)"""
     return torch.tensor([[(v >> (62 * j)) & ((1 << 62) - 1) for j in range(5)] for v in vals], dtype=torch.int64)
@@ -88,7 +96,7 @@ def test_sharded_sumcheck_equals_single(kind, bn, world):
     q = P.random_fr_array(bn + 2)[2:]
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 29500 + (os.getpid() % 2000)
+    port = _free_port()
     mp.spawn(_worker, args=(world, port, bn, kind, q, out), nprocs=world, join=True)
     assert dict(out) == {g: 1 for g in range(world)}
 
@@ -126,7 +134,7 @@ def _upload_worker(rank, world, port, n, out):
 def test_sharded_upload_all_to_all(world, n):
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 31500 + (os.getpid() % 2000)
+    port = _free_port()
     mp.spawn(_upload_worker, args=(world, port, n, out), nprocs=world, join=True)
     assert dict(out) == {g: 1 for g in range(world)}
 
@@ -208,6 +216,6 @@ def test_leader_transcript_equals_single(bn, world, leader):
     q = P.random_fr_array(bn + 2)[2:]
     mgr = mp.Manager()
     out = mgr.dict()
-    port = 33500 + (os.getpid() % 2000)
+    port = _free_port()
     mp.spawn(_leader_worker, args=(world, port, bn, leader, q, out), nprocs=world, join=True)
     assert dict(out) == {g: 1 for g in range(world)}
