@@ -1,0 +1,425 @@
+// libgkrb200ec.so: host driver and C ABI of the G1 multi-exponentiation (include/gkrb200_ec.h).
+// The kernels are the per-index bodies of msm.cuh run as grids of 128-thread blocks; this file adds the CUDA executor, the
+// context (stream, grow-only workspace, resident bases), and the host-side tail of InitialRandomnessHint.Call
+// (prover/gadget/hints.go:147-192: RawBytes, legacy Keccak-256, fr.SetBytes).
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../../include/gkrb200_ec.h"
+#include "msm.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU_TRY(x)                                                                                              \
+    do {                                                                                                       \
+        cudaError_t e_ = (x);                                                                                  \
+        if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? GKRB200EC_ERR_OOM : GKRB200EC_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class K, class... A>
+__global__ void __launch_bounds__(128) k_each(size_t n, A... a) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) K::run(i, a...);
+}
+
+struct CudaExec {
+    cudaStream_t st;
+    cudaError_t err = cudaSuccess;
+    template <class K, class... A>
+    int launch(size_t n, A... a) {
+        if (n == 0) return 0;
+        const unsigned blocks = (unsigned)((n + 127) / 128);
+        k_each<K, A...><<<blocks, 128, 0, st>>>(n, a...);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        return 1;
+    }
+    void zero(void* p, size_t bytes) {
+        const cudaError_t e = cudaMemsetAsync(p, 0, bytes, st);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+    }
+};
+
+}  // namespace
+
+struct gkrb200ec_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    unsigned char* ws = nullptr;
+    size_t ws_bytes = 0;
+    uint64_t* d_scalars = nullptr;  // staging for host scalars
+    size_t sc_cap = 0;
+    uint64_t* d_tmp_points = nullptr;  // staging for one-shot host points
+    size_t tp_cap = 0;
+    uint64_t* d_small = nullptr;  // 2 input points + 16 result words for gkrb200ec_g1_add
+    uint64_t* h_pin = nullptr;    // pinned: 16 result words + error flag
+    struct Slot {
+        uint64_t* d = nullptr;
+        size_t n = 0;
+    } slots[GKRB200EC_MAX_SLOTS];
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int c_force = 0, T_force = 0;
+    gkrb200ec_stats st{};
+};
+
+namespace {
+
+int ensure(gkrb200ec_ctx* c, void** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return 0;
+    if (*p) CU_TRY(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    CU_TRY(cudaMalloc(p, bytes));
+    *cap = bytes;
+    (void)c;
+    return 0;
+}
+
+// out16: affine result, Montgomery (8 words) then regular form (8 words)
+int run_msm(gkrb200ec_ctx* c, const uint64_t* d_points, const uint64_t* d_scalars, size_t n, int form, uint64_t* out16) {
+    if (n == 0) {
+        memset(out16, 0, 16 * sizeof(uint64_t));
+        return 0;
+    }
+    const ec::MsmPlan pl = ec::msm_make_plan(n, form == GKRB200EC_SCALARS_MONTGOMERY, c->c_force, c->T_force);
+    if ((uint64_t)pl.n * pl.W >= 0xffffffffull) return fail(GKRB200EC_ERR_ARG, "multiexp: %zu points x %u windows does not fit 32-bit entry offsets", n, pl.W);
+    const ec::MsmWorkspace ws = ec::msm_layout(pl);
+    {
+        void* p = c->ws;
+        const int rc = ensure(c, &p, &c->ws_bytes, ws.bytes);
+        c->ws = (unsigned char*)p;
+        if (rc) return rc;
+    }
+    CudaExec ex{c->stream};
+    CU_TRY(cudaEventRecord(c->e0, c->stream));
+    const int launches = ec::msm_enqueue(ex, pl, ws, c->ws, d_points, d_scalars);
+    CU_TRY(cudaEventRecord(c->e1, c->stream));
+    if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "multiexp launch: %s", cudaGetErrorString(ex.err));
+    CU_TRY(cudaMemcpyAsync(c->h_pin, c->ws + ws.out, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->h_pin + 16, c->ws + ws.err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, c->e0, c->e1));
+    c->st.launches_total += (uint64_t)launches;
+    c->st.msm_calls++;
+    c->st.last_n = pl.n, c->st.last_c = pl.c, c->st.last_windows = pl.W, c->st.last_task_size = pl.T;
+    c->st.last_tasks_max = pl.max_tasks;
+    c->st.workspace_bytes = c->ws_bytes;
+    c->st.d2h_bytes += 16 * sizeof(uint64_t) + sizeof(uint32_t);
+    c->st.last_device_ms = ms;
+    const uint32_t flag = (uint32_t)c->h_pin[16];
+    if (flag & ec::MSM_ERR_SCALAR_RANGE) return fail(GKRB200EC_ERR_ARG, "multiexp: a regular-form scalar is not reduced (>= q)");
+    if (flag) return fail(GKRB200EC_ERR_CUDA, "multiexp: internal digit overflow (flag %u)", flag);
+    memcpy(out16, c->h_pin, 16 * sizeof(uint64_t));
+    return 0;
+}
+
+int stage_scalars(gkrb200ec_ctx* c, const uint64_t* scalars, size_t n) {
+    void* p = c->d_scalars;
+    const int rc = ensure(c, &p, &c->sc_cap, n * 32);
+    c->d_scalars = (uint64_t*)p;
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(c->d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, c->stream));
+    c->st.h2d_bytes += n * 32;
+    return 0;
+}
+
+int check_slot(gkrb200ec_ctx* c, int slot, size_t n) {
+    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
+    if (slot < 0 || slot >= GKRB200EC_MAX_SLOTS) return fail(GKRB200EC_ERR_ARG, "base slot %d out of range", slot);
+    if (n > c->slots[slot].n) return fail(GKRB200EC_ERR_ARG, "%zu scalars for %zu bases in slot %d", n, c->slots[slot].n, slot);
+    return 0;
+}
+
+int add_points(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out16) {
+    CU_TRY(cudaMemcpyAsync(c->d_small, a, 64, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->d_small + 8, b, 64, cudaMemcpyHostToDevice, c->stream));
+    CudaExec ex{c->stream};
+    c->st.launches_total += (uint64_t)ex.launch<ec::KAddAffine>(1, (const uint64_t*)c->d_small, (const uint64_t*)(c->d_small + 8), c->d_small + 16);
+    if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "g1 add launch: %s", cudaGetErrorString(ex.err));
+    CU_TRY(cudaMemcpyAsync(c->h_pin, c->d_small + 16, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    memcpy(out16, c->h_pin, 16 * sizeof(uint64_t));
+    c->st.h2d_bytes += 128, c->st.d2h_bytes += 128;
+    return 0;
+}
+
+// ---- host side of DeriveRandomnessFromPoint -----------------------------------------------------------------------------------
+// legacy Keccak-256: Keccak-f[1600], rate 136 bytes, multi-rate padding with domain byte 0x01 (not SHA-3's 0x06)
+void keccak_f1600(uint64_t* a) {
+    static const uint64_t RC[24] = {0x0000000000000001ull, 0x0000000000008082ull, 0x800000000000808aull, 0x8000000080008000ull, 0x000000000000808bull,
+                                    0x0000000080000001ull, 0x8000000080008081ull, 0x8000000000008009ull, 0x000000000000008aull, 0x0000000000000088ull,
+                                    0x0000000080008009ull, 0x000000008000000aull, 0x000000008000808bull, 0x800000000000008bull, 0x8000000000008089ull,
+                                    0x8000000000008003ull, 0x8000000000008002ull, 0x8000000000000080ull, 0x000000000000800aull, 0x800000008000000aull,
+                                    0x8000000080008081ull, 0x8000000000008080ull, 0x0000000080000001ull, 0x8000000080008008ull};
+    // rho offsets and pi destinations along the 24-lane cycle starting at lane 1
+    static const int RHO[24] = {1, 3, 6, 10, 15, 21, 28, 36, 45, 55, 2, 14, 27, 41, 56, 8, 25, 43, 62, 18, 39, 61, 20, 44};
+    static const int PI[24] = {10, 7, 11, 17, 18, 3, 5, 16, 8, 21, 24, 4, 15, 23, 19, 13, 12, 2, 20, 14, 22, 9, 6, 1};
+    for (int round = 0; round < 24; round++) {
+        uint64_t bc[5];
+        for (int x = 0; x < 5; x++) bc[x] = a[x] ^ a[x + 5] ^ a[x + 10] ^ a[x + 15] ^ a[x + 20];
+        for (int x = 0; x < 5; x++) {
+            const uint64_t r = bc[(x + 1) % 5];
+            const uint64_t t = bc[(x + 4) % 5] ^ ((r << 1) | (r >> 63));
+            for (int y = 0; y < 25; y += 5) a[y + x] ^= t;
+        }
+        uint64_t t = a[1];
+        for (int i = 0; i < 24; i++) {
+            const int j = PI[i];
+            const uint64_t keep = a[j];
+            a[j] = (t << RHO[i]) | (t >> (64 - RHO[i]));
+            t = keep;
+        }
+        for (int y = 0; y < 25; y += 5) {
+            for (int x = 0; x < 5; x++) bc[x] = a[y + x];
+            for (int x = 0; x < 5; x++) a[y + x] = bc[x] ^ (~bc[(x + 1) % 5] & bc[(x + 2) % 5]);
+        }
+        a[0] ^= RC[round];
+    }
+}
+void keccak256(const uint8_t* data, size_t len, uint8_t* out) {
+    uint64_t a[25];
+    memset(a, 0, sizeof a);
+    const size_t rate = 136;
+    uint8_t block[136];
+    size_t done = 0;
+    bool last = false;
+    while (!last) {
+        const size_t take = len - done < rate ? len - done : rate;
+        last = take < rate;
+        memset(block, 0, rate);
+        if (take) memcpy(block, data + done, take);
+        if (last) {
+            block[take] ^= 0x01;
+            block[rate - 1] ^= 0x80;
+        }
+        for (size_t i = 0; i < rate / 8; i++) {
+            uint64_t w;
+            memcpy(&w, block + 8 * i, 8);  // little-endian host (x86-64 / aarch64)
+            a[i] ^= w;
+        }
+        keccak_f1600(a);
+        done += take;
+    }
+    memcpy(out, a, 32);
+}
+// regular-form affine words (X: r[0..4), Y: r[4..8)) -> RawBytes
+void raw_bytes_from_regular(const uint64_t* r, uint8_t* out) {
+    bool inf = true;
+    for (int i = 0; i < 8; i++) inf = inf && r[i] == 0;
+    memset(out, 0, 64);
+    if (inf) {
+        out[0] = 0x40;  // mUncompressedInfinity
+        return;
+    }
+    for (int i = 0; i < 32; i++) {
+        out[31 - i] = (uint8_t)(r[i / 8] >> (8 * (i % 8)));
+        out[63 - i] = (uint8_t)(r[4 + i / 8] >> (8 * (i % 8)));
+    }
+}
+// fr.SetBytes of a 32-byte big-endian value, returned in regular form: the integer mod q
+void fr_set_bytes_regular(const uint8_t* be, uint64_t* out) {
+    ec::Big8 v;
+    for (int i = 0; i < 8; i++) v.v[i] = (uint32_t)be[31 - 4 * i] | ((uint32_t)be[30 - 4 * i] << 8) | ((uint32_t)be[29 - 4 * i] << 16) | ((uint32_t)be[28 - 4 * i] << 24);
+    for (int k = 0; k < 6 && !ec::f_is_canonical<ec::FrMod>(v); k++) {  // 2^256 / q < 6
+        ec::Big8 s;
+        (void)ec::f_sub_mod<ec::FrMod>(s, v);
+        v = s;
+    }
+    ec::big_store(out, v);
+}
+void derive_from_regular(const uint64_t* reg8, uint64_t* out) {
+    uint8_t raw[64], h[32];
+    raw_bytes_from_regular(reg8, raw);
+    keccak256(raw, 64, h);
+    fr_set_bytes_regular(h, out);
+}
+void regular_from_mont(const uint64_t* g1, uint64_t* reg8) {
+    const ec::Big8 x = ec::f_from_mont<ec::Fp>(ec::big_load(g1)), y = ec::f_from_mont<ec::Fp>(ec::big_load(g1 + 4));
+    ec::big_store(reg8, x);
+    ec::big_store(reg8 + 4, y);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* gkrb200ec_version(void) { return "gkrb200ec 0.1 (sm_100a; G1 bucket method, XYZZ, signed digits)"; }
+const char* gkrb200ec_last_error(void) { return g_err; }
+
+int gkrb200ec_init(gkrb200ec_ctx** out, int device, void* stream) {
+    if (!out) return fail(GKRB200EC_ERR_ARG, "null ctx pointer");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(GKRB200EC_ERR_CUDA, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(GKRB200EC_ERR_ARG, "device %d of %d", device, ndev);
+    CU_TRY(cudaSetDevice(device));
+    gkrb200ec_ctx* c = new gkrb200ec_ctx();
+    c->device = device;
+    int rc = 0;
+    auto step = [&](cudaError_t e, const char* what) {
+        if (rc == 0 && e != cudaSuccess) rc = fail(GKRB200EC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    };
+    if (stream) c->stream = (cudaStream_t)stream;
+    else {
+        step(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream");
+        c->own_stream = rc == 0;
+    }
+    step(cudaMalloc((void**)&c->d_small, 32 * sizeof(uint64_t)), "scratch");
+    step(cudaMallocHost((void**)&c->h_pin, 32 * sizeof(uint64_t)), "pinned result");
+    step(cudaEventCreate(&c->e0), "event");
+    step(cudaEventCreate(&c->e1), "event");
+    if (rc) {
+        gkrb200ec_free(c);
+        return rc;
+    }
+    *out = c;
+    return 0;
+}
+
+void gkrb200ec_free(gkrb200ec_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& s : c->slots)
+        if (s.d) cudaFree(s.d);
+    if (c->ws) cudaFree(c->ws);
+    if (c->d_scalars) cudaFree(c->d_scalars);
+    if (c->d_tmp_points) cudaFree(c->d_tmp_points);
+    if (c->d_small) cudaFree(c->d_small);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    if (c->e0) cudaEventDestroy(c->e0);
+    if (c->e1) cudaEventDestroy(c->e1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int gkrb200ec_g1_set_bases(gkrb200ec_ctx* c, int slot, const uint64_t* points, size_t n) {
+    if (const int rc = check_slot(c, slot, 0)) return rc;
+    if (n && !points) return fail(GKRB200EC_ERR_ARG, "null points");
+    if (n > GKRB200EC_MAX_POINTS) return fail(GKRB200EC_ERR_ARG, "%zu points: at most %u", n, GKRB200EC_MAX_POINTS);
+    CU_TRY(cudaSetDevice(c->device));
+    auto& s = c->slots[slot];
+    if (s.d) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        CU_TRY(cudaFree(s.d));
+        s.d = nullptr, s.n = 0;
+    }
+    if (n == 0) return 0;
+    CU_TRY(cudaMalloc((void**)&s.d, n * 64));
+    CU_TRY(cudaMemcpyAsync(s.d, points, n * 64, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    s.n = n;
+    c->st.h2d_bytes += n * 64;
+    return 0;
+}
+
+int gkrb200ec_g1_multiexp_device(gkrb200ec_ctx* c, int slot, const void* d_scalars, size_t n, int form, uint64_t* out) {
+    if (const int rc = check_slot(c, slot, n)) return rc;
+    if (!out || (n && !d_scalars)) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    if (form != GKRB200EC_SCALARS_REGULAR && form != GKRB200EC_SCALARS_MONTGOMERY) return fail(GKRB200EC_ERR_ARG, "scalar form %d", form);
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t r[16];
+    if (const int rc = run_msm(c, c->slots[slot].d, (const uint64_t*)d_scalars, n, form, r)) return rc;
+    memcpy(out, r, 64);
+    return 0;
+}
+
+int gkrb200ec_g1_multiexp(gkrb200ec_ctx* c, int slot, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
+    if (const int rc = check_slot(c, slot, n)) return rc;
+    if (!out || (n && !scalars)) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    CU_TRY(cudaSetDevice(c->device));
+    if (n)
+        if (const int rc = stage_scalars(c, scalars, n)) return rc;
+    return gkrb200ec_g1_multiexp_device(c, slot, c->d_scalars, n, form, out);
+}
+
+int gkrb200ec_g1_multiexp_points(gkrb200ec_ctx* c, const uint64_t* points, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
+    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
+    if (!out || (n && (!points || !scalars))) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    if (n > GKRB200EC_MAX_POINTS) return fail(GKRB200EC_ERR_ARG, "%zu points: at most %u", n, GKRB200EC_MAX_POINTS);
+    if (form != GKRB200EC_SCALARS_REGULAR && form != GKRB200EC_SCALARS_MONTGOMERY) return fail(GKRB200EC_ERR_ARG, "scalar form %d", form);
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t r[16];
+    if (n) {
+        void* p = c->d_tmp_points;
+        const int rc = ensure(c, &p, &c->tp_cap, n * 64);
+        c->d_tmp_points = (uint64_t*)p;
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(c->d_tmp_points, points, n * 64, cudaMemcpyHostToDevice, c->stream));
+        c->st.h2d_bytes += n * 64;
+        if (const int rc2 = stage_scalars(c, scalars, n)) return rc2;
+    }
+    if (const int rc = run_msm(c, c->d_tmp_points, c->d_scalars, n, form, r)) return rc;
+    memcpy(out, r, 64);
+    return 0;
+}
+
+int gkrb200ec_g1_add(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    if (!c || !a || !b || !out) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t r[16];
+    if (const int rc = add_points(c, a, b, r)) return rc;
+    memcpy(out, r, 64);
+    return 0;
+}
+
+int gkrb200ec_initial_randomness(gkrb200ec_ctx* c, int slot_pub, const uint64_t* scalars_pub, size_t n_pub, int slot_priv, const uint64_t* scalars_priv,
+                                 size_t n_priv, int form, uint64_t* krs_gkr_priv_out, uint64_t* initial_randomness_out) {
+    if (!krs_gkr_priv_out || !initial_randomness_out) return fail(GKRB200EC_ERR_ARG, "null output");
+    uint64_t krs[8], priv[8], sum[16];
+    if (const int rc = gkrb200ec_g1_multiexp(c, slot_pub, scalars_pub, n_pub, form, krs)) return rc;        // hints.go:182
+    if (const int rc = gkrb200ec_g1_multiexp(c, slot_priv, scalars_priv, n_priv, form, priv)) return rc;     // hints.go:183
+    if (const int rc = add_points(c, krs, priv, sum)) return rc;                                             // hints.go:184
+    memcpy(krs_gkr_priv_out, priv, 64);                                                                      // hints.go:186
+    derive_from_regular(sum + 8, initial_randomness_out);                                                    // hints.go:188-189
+    return 0;
+}
+
+int gkrb200ec_g1_raw_bytes(const uint64_t* g1, uint8_t out[64]) {
+    if (!g1 || !out) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    uint64_t reg[8];
+    regular_from_mont(g1, reg);
+    raw_bytes_from_regular(reg, out);
+    return 0;
+}
+int gkrb200ec_keccak256(const uint8_t* data, size_t len, uint8_t out[32]) {
+    if ((len && !data) || !out) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    keccak256(data, len, out);
+    return 0;
+}
+int gkrb200ec_derive_randomness_from_point(const uint64_t* g1, uint64_t* out) {
+    if (!g1 || !out) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    uint64_t reg[8];
+    regular_from_mont(g1, reg);
+    derive_from_regular(reg, out);
+    return 0;
+}
+
+int gkrb200ec_set_plan(gkrb200ec_ctx* c, int window_bits, int task_size) {
+    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
+    if (window_bits != 0 && (window_bits < 2 || window_bits > 16)) return fail(GKRB200EC_ERR_ARG, "window width %d outside 2..16", window_bits);
+    if (task_size < 0) return fail(GKRB200EC_ERR_ARG, "task size %d", task_size);
+    c->c_force = window_bits;
+    c->T_force = task_size;
+    return 0;
+}
+int gkrb200ec_get_stats(gkrb200ec_ctx* c, gkrb200ec_stats* out) {
+    if (!c || !out) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    *out = c->st;
+    return 0;
+}
+
+}  // extern "C"

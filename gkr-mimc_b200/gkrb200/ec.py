@@ -1,0 +1,202 @@
+"""Host-side mirror of the Groth16-side G1 operations of the gkr-mimc prover over libgkrb200ec.so.
+
+    reference (Go)                                                        here
+    --------------------------------------------------------------------  ---------------------------------------------
+    pk.pubKGkr / pk.privKGkrSigma []bn254.G1Affine (setup.go:32,116-121)   EcContext.SetBases(slot, points)
+    G1Affine.MultiExp(points, scalars, ecc.MultiExpConfig{})               EcContext.MultiExp(slot, scalars) / MultiExpPoints
+    G1Affine.Add (hints.go:184)                                            EcContext.Add(a, b)
+    DeriveRandomnessFromPoint(g1) (hints.go:147-159)                       DeriveRandomnessFromPoint(g1)
+    InitialRandomnessHint.Call (hints.go:162-192)                          EcContext.InitialRandomnessHint(...)
+
+Points are numpy uint64 arrays (..., 8) = []bn254.G1Affine (X, Y; Montgomery; infinity all zero), scalars (..., 4) = []fr.Element.
+Everything that touches a point array runs on the GPU; the library fails loudly without one.  There is no CPU fallback.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_PKG)
+SO_PATH = os.path.join(ROOT, "libgkrb200ec.so")
+
+SCALARS_REGULAR, SCALARS_MONTGOMERY = 0, 1
+MAX_SLOTS = 16
+
+
+class EcStats(ctypes.Structure):
+    _fields_ = [
+        ("launches_total", ctypes.c_uint64),
+        ("msm_calls", ctypes.c_uint64),
+        ("last_n", ctypes.c_uint32),
+        ("last_c", ctypes.c_uint32),
+        ("last_windows", ctypes.c_uint32),
+        ("last_task_size", ctypes.c_uint32),
+        ("last_tasks_max", ctypes.c_uint64),
+        ("workspace_bytes", ctypes.c_uint64),
+        ("h2d_bytes", ctypes.c_uint64),
+        ("d2h_bytes", ctypes.c_uint64),
+        ("last_device_ms", ctypes.c_double),
+    ]
+
+
+class GkrB200EcError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("gkrb200ec error %d: %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError("gkrb200: %s is missing. Build it with `make -C %s` (or __graft_entry__.build()); there is no CPU fallback."
+                           % (SO_PATH, ROOT))
+    L = ctypes.CDLL(SO_PATH)
+    vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    L.gkrb200ec_version.restype = ctypes.c_char_p
+    L.gkrb200ec_last_error.restype = ctypes.c_char_p
+    L.gkrb200ec_init.argtypes = [ctypes.POINTER(vp), i32, vp]
+    L.gkrb200ec_free.argtypes = [vp]
+    L.gkrb200ec_free.restype = None
+    L.gkrb200ec_g1_set_bases.argtypes = [vp, i32, vp, sz]
+    L.gkrb200ec_g1_multiexp.argtypes = [vp, i32, vp, sz, i32, vp]
+    L.gkrb200ec_g1_multiexp_device.argtypes = [vp, i32, vp, sz, i32, vp]
+    L.gkrb200ec_g1_multiexp_points.argtypes = [vp, vp, vp, sz, i32, vp]
+    L.gkrb200ec_initial_randomness.argtypes = [vp, i32, vp, sz, i32, vp, sz, i32, vp, vp]
+    L.gkrb200ec_g1_add.argtypes = [vp, vp, vp, vp]
+    L.gkrb200ec_g1_raw_bytes.argtypes = [vp, vp]
+    L.gkrb200ec_keccak256.argtypes = [vp, sz, vp]
+    L.gkrb200ec_derive_randomness_from_point.argtypes = [vp, vp]
+    L.gkrb200ec_set_plan.argtypes = [vp, i32, i32]
+    L.gkrb200ec_get_stats.argtypes = [vp, ctypes.POINTER(EcStats)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise GkrB200EcError(rc, lib().gkrb200ec_last_error().decode("utf-8", "replace"))
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def g1_array(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.shape[-1] != 8:
+        raise ValueError("G1Affine points must have a trailing dimension of 8 uint64 limbs")
+    return a
+
+
+def fr_array(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.shape[-1] != 4:
+        raise ValueError("field elements must have a trailing dimension of 4 uint64 limbs")
+    return a
+
+
+# ---- host-only pieces (no device) -------------------------------------------------------------------------------------------
+def RawBytes(g1) -> bytes:
+    """G1Affine.RawBytes"""
+    g1 = g1_array(g1).reshape(8)
+    out = (ctypes.c_uint8 * 64)()
+    check(lib().gkrb200ec_g1_raw_bytes(_p(g1), out))
+    return bytes(out)
+
+
+def LegacyKeccak256(data: bytes) -> bytes:
+    """sha3.NewLegacyKeccak256().Write(data).Sum(nil)"""
+    buf = (ctypes.c_uint8 * max(1, len(data))).from_buffer_copy(data if data else b"\0")
+    out = (ctypes.c_uint8 * 32)()
+    check(lib().gkrb200ec_keccak256(buf, len(data), out))
+    return bytes(out)
+
+
+def DeriveRandomnessFromPoint(g1):
+    """prover/gadget/hints.go:147-159 -> (4,) uint64, REGULAR form (the big.Int the hint returns)"""
+    g1 = g1_array(g1).reshape(8)
+    out = np.zeros(4, dtype=np.uint64)
+    check(lib().gkrb200ec_derive_randomness_from_point(_p(g1), _p(out)))
+    return out
+
+
+# ---- device context -----------------------------------------------------------------------------------------------------------
+class EcContext:
+    def __init__(self, device=0, stream=None):
+        self._h = ctypes.c_void_p()
+        check(lib().gkrb200ec_init(ctypes.byref(self._h), device, ctypes.c_void_p(stream) if stream else None))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().gkrb200ec_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def SetBases(self, slot, points):
+        """upload proving-key points once (pk.pubKGkr, pk.privKGkrSigma, pk.privKNotGkr, pk.G1.A ...)"""
+        points = g1_array(points).reshape(-1, 8)
+        check(lib().gkrb200ec_g1_set_bases(self._h, slot, _p(points) if points.shape[0] else None, points.shape[0]))
+
+    def MultiExp(self, slot, scalars, form=SCALARS_REGULAR):
+        """res.MultiExp(bases[slot][:len(scalars)], scalars, ecc.MultiExpConfig{}) -> (8,) G1Affine"""
+        scalars = fr_array(scalars).reshape(-1, 4)
+        out = np.zeros(8, dtype=np.uint64)
+        check(lib().gkrb200ec_g1_multiexp(self._h, slot, _p(scalars) if scalars.shape[0] else None, scalars.shape[0], form, _p(out)))
+        return out
+
+    def MultiExpDevice(self, slot, d_scalars_ptr, n, form=SCALARS_REGULAR):
+        """scalars already in device memory (raw pointer, 16-byte aligned, n x 4 uint64)"""
+        out = np.zeros(8, dtype=np.uint64)
+        check(lib().gkrb200ec_g1_multiexp_device(self._h, slot, ctypes.c_void_p(d_scalars_ptr), n, form, _p(out)))
+        return out
+
+    def MultiExpPoints(self, points, scalars, form=SCALARS_REGULAR):
+        """one-shot: exactly G1Affine.MultiExp(points, scalars, cfg)"""
+        points, scalars = g1_array(points).reshape(-1, 8), fr_array(scalars).reshape(-1, 4)
+        if points.shape[0] != scalars.shape[0]:
+            raise ValueError("len(points) != len(scalars)")  # gnark-crypto returns an error here
+        out = np.zeros(8, dtype=np.uint64)
+        n = points.shape[0]
+        check(lib().gkrb200ec_g1_multiexp_points(self._h, _p(points) if n else None, _p(scalars) if n else None, n, form, _p(out)))
+        return out
+
+    def Add(self, a, b):
+        a, b = g1_array(a).reshape(8), g1_array(b).reshape(8)
+        out = np.zeros(8, dtype=np.uint64)
+        check(lib().gkrb200ec_g1_add(self._h, _p(a), _p(b), _p(out)))
+        return out
+
+    def InitialRandomnessHint(self, slot_pub, scalars_pub, slot_priv, scalars_priv, form=SCALARS_REGULAR):
+        """prover/gadget/hints.go:162-192 -> (KrsGkrPriv (8,), initialRandomness (4,) regular form)"""
+        sp, sq = fr_array(scalars_pub).reshape(-1, 4), fr_array(scalars_priv).reshape(-1, 4)
+        krs_priv = np.zeros(8, dtype=np.uint64)
+        rnd = np.zeros(4, dtype=np.uint64)
+        check(lib().gkrb200ec_initial_randomness(self._h, slot_pub, _p(sp) if sp.shape[0] else None, sp.shape[0], slot_priv,
+                                                 _p(sq) if sq.shape[0] else None, sq.shape[0], form, _p(krs_priv), _p(rnd)))
+        return krs_priv, rnd
+
+    def set_plan(self, window_bits=0, task_size=0):
+        check(lib().gkrb200ec_set_plan(self._h, window_bits, task_size))
+
+    def stats(self):
+        st = EcStats()
+        check(lib().gkrb200ec_get_stats(self._h, ctypes.byref(st)))
+        return st

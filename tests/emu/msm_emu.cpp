@@ -1,0 +1,135 @@
+// CPU emulation of the multi-exponentiation kernels -- TEST INFRASTRUCTURE, never shipped or loaded by the product.
+//
+// Compiles the product headers gkr-mimc_b200/csrc/ec/{field,g1,msm}.cuh with a plain C++ compiler: every kernel body is a function of
+// its thread index, and the executor below runs each "launch" as a loop.  Host-side, field.cuh's carry-chain primitives are plain
+// 64-bit C++ with the semantics of the inline-PTX ones the device uses (those are exercised on the GPU by every GKR parity test).
+// tests/test_msm_cpu.py drives this against the oracle, so the digit decomposition, counting sort, task splitting, XYZZ formulas
+// with all exceptional cases, window reduction and the driver's launch sequence are checked without a GPU; tests/test_zz_msm_gpu.py
+// then checks the real library on the device against the same oracle.
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../gkr-mimc_b200/csrc/ec/msm.cuh"
+
+namespace {
+struct HostExec {
+    template <class K, class... A>
+    int launch(size_t n, A... a) {
+        if (n == 0) return 0;
+        for (size_t i = 0; i < n; i++) K::run(i, a...);
+        return 1;
+    }
+    // a second order of execution: threads run from the last to the first (shakes out order dependence of the atomics)
+    bool reverse = false;
+    void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+};
+struct HostExecReverse {
+    template <class K, class... A>
+    int launch(size_t n, A... a) {
+        for (size_t i = n; i-- > 0;) K::run(i, a...);
+        return n ? 1 : 0;
+    }
+    void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
+};
+using namespace ec;
+Big8 ld(const uint64_t* p) { return big_load(p); }
+}  // namespace
+
+extern "C" {
+
+// op: 0 mul, 1 sqr, 2 add, 3 sub, 4 inv, 5 from_mont, 6 to_mont, 7 out-of-line mul;  field: 0 = Fp, 1 = Fr
+void emu_field_op(int field, int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+    for (size_t i = 0; i < n; i++) {
+        const Big8 x = ld(a + 4 * i), y = b ? ld(b + 4 * i) : big_zero();
+        Big8 r = big_zero();
+        if (field == 0) {
+            switch (op) {
+                case 0: r = f_mul<FpMod>(x, y); break;
+                case 1: r = f_sqr<FpMod>(x); break;
+                case 2: r = f_add<FpMod>(x, y); break;
+                case 3: r = f_sub<FpMod>(x, y); break;
+                case 4: r = f_inv<FpMod>(x); break;
+                case 5: r = f_from_mont<FpMod>(x); break;
+                case 6: r = f_to_mont<FpMod>(x); break;
+                case 7: r = f_mulc<FpMod>(x, y); break;
+            }
+        } else {
+            switch (op) {
+                case 0: r = f_mul<FrMod>(x, y); break;
+                case 1: r = f_sqr<FrMod>(x); break;
+                case 2: r = f_add<FrMod>(x, y); break;
+                case 3: r = f_sub<FrMod>(x, y); break;
+                case 4: r = f_inv<FrMod>(x); break;
+                case 5: r = f_from_mont<FrMod>(x); break;
+                case 6: r = f_to_mont<FrMod>(x); break;
+                case 7: r = f_mulc<FrMod>(x, y); break;
+            }
+        }
+        big_store(out + 4 * i, r);
+    }
+}
+
+// XYZZ operations on affine inputs, result affine (Montgomery).  op: 0 madd (a as XYZZ + affine b), 1 full add, 2 double a,
+// 3 k * a with k = b[0] (small), 4 madd after re-randomising a's representation (a = 3a - 2a path: a non-trivial ZZ)
+void emu_g1_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    const G1Affine pa = g1_aff_load(a);
+    G1X r = g1x_inf();
+    if (op == 0) r = g1x_add_affine<MulInline>(g1x_from_affine(pa), g1_aff_load(b));
+    else if (op == 1) r = g1x_add<MulCall>(g1x_from_affine(pa), g1x_from_affine(g1_aff_load(b)));
+    else if (op == 2) r = g1x_dbl<MulCall>(g1x_from_affine(pa));
+    else if (op == 3) r = g1x_mul_small<MulCall>(g1x_from_affine(pa), (uint32_t)b[0]);
+    else if (op == 4) {
+        // a written as (2a + 2a) - 3a ... : build a with ZZ != 1 through doublings and additions, then add b
+        G1X t = g1x_dbl<MulInline>(g1x_from_affine(pa));       // 2a
+        t = g1x_add_affine<MulInline>(t, pa);                   // 3a
+        G1Affine na = pa;
+        na.y = f_neg<Fp>(na.y);
+        t = g1x_add_affine<MulInline>(t, na);                   // 2a
+        t = g1x_add_affine<MulInline>(t, na);                   // a, ZZ != 1
+        r = g1x_add_affine<MulInline>(t, g1_aff_load(b));       // a + b incl. the doubling / cancellation cases on a non-trivial ZZ
+    } else if (op == 5) {
+        G1X t = g1x_dbl<MulCall>(g1x_from_affine(pa));
+        G1Affine na = pa;
+        na.y = f_neg<Fp>(na.y);
+        t = g1x_add_affine<MulCall>(t, na);  // a, ZZ != 1
+        G1X u = g1x_dbl<MulCall>(g1x_from_affine(g1_aff_load(b)));
+        G1Affine nb = g1_aff_load(b);
+        nb.y = f_neg<Fp>(nb.y);
+        u = g1x_add_affine<MulCall>(u, nb);  // b, ZZ != 1
+        r = g1x_add<MulCall>(t, u);
+    }
+    g1_aff_store(out, g1x_to_affine(r));
+}
+
+// The whole multi-exponentiation through msm_enqueue on the host executor.  out16 as the device writes it; returns the error flag,
+// or -1 when the plan does not fit.  reverse != 0 runs every launch's threads in descending order.
+int emu_msm(const uint64_t* points, const uint64_t* scalars, size_t n, int scalars_mont, int c_force, int t_force, int reverse, uint64_t* out16,
+            uint32_t* plan_out) {
+    if (n == 0) {
+        memset(out16, 0, 128);
+        return 0;
+    }
+    const MsmPlan pl = msm_make_plan(n, scalars_mont, c_force, t_force);
+    if (plan_out) plan_out[0] = pl.c, plan_out[1] = pl.W, plan_out[2] = pl.T, plan_out[3] = pl.L, plan_out[4] = pl.nchunks, plan_out[5] = (uint32_t)pl.max_tasks;
+    if ((uint64_t)pl.n * pl.W >= 0xffffffffull) return -1;
+    const MsmWorkspace ws = msm_layout(pl);
+    std::vector<unsigned char> buf(ws.bytes + 256, 0xA5);  // poisoned: nothing may rely on zero-initialised workspace
+    unsigned char* base = (unsigned char*)(((uintptr_t)buf.data() + 255) & ~(uintptr_t)255);
+    int launches;
+    if (reverse) {
+        HostExecReverse ex;
+        launches = msm_enqueue(ex, pl, ws, base, points, scalars);
+    } else {
+        HostExec ex;
+        launches = msm_enqueue(ex, pl, ws, base, points, scalars);
+    }
+    (void)launches;
+    memcpy(out16, base + ws.out, 128);
+    uint32_t flag;
+    memcpy(&flag, base + ws.err, 4);
+    return (int)flag;
+}
+
+void emu_g1_add_affine(const uint64_t* a, const uint64_t* b, uint64_t* out16) { KAddAffine::run(0, a, b, out16); }
+}
