@@ -1,7 +1,7 @@
-// libgkrb200ec.so: host driver and C ABI of the G1 multi-exponentiation (include/gkrb200_ec.h).
-// The kernels are the per-index bodies of msm.cuh run as grids of 128-thread blocks; this file adds the CUDA executor, the
-// context (stream, grow-only workspace, resident bases), and the host-side tail of InitialRandomnessHint.Call
-// (prover/gadget/hints.go:147-192: RawBytes, legacy Keccak-256, fr.SetBytes).
+// libgkrb200ec.so: host driver and C ABI of the Groth16-side operations (include/gkrb200_ec.h): the G1 multi-exponentiation and
+// the FFTs of computeH.  The kernels are the per-index bodies of msm.cuh and ntt.cuh run as grids of 128-thread blocks; this file
+// adds the CUDA executor, the context (stream, grow-only workspaces, resident bases, the resident fft.Domain), and the host-side
+// tail of InitialRandomnessHint.Call (prover/gadget/hints.go:147-192: RawBytes, legacy Keccak-256, fr.SetBytes).
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -10,6 +10,7 @@
 
 #include "../../../include/gkrb200_ec.h"
 #include "msm.cuh"
+#include "ntt.cuh"
 
 namespace {
 
@@ -71,6 +72,12 @@ struct gkrb200ec_ctx {
     } slots[GKRB200EC_MAX_SLOTS];
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int c_force = 0, T_force = 0;
+    // fft.Domain resident on the device: twiddle tables + split coset tables in one buffer; three work arrays for computeH
+    bool have_domain = false;
+    ec::NttDomainDev dom{};
+    unsigned char* dom_buf = nullptr;
+    uint64_t* d_abc = nullptr;  // 3 x cardinality elements
+    size_t abc_cap = 0;
     gkrb200ec_stats st{};
 };
 
@@ -252,11 +259,99 @@ void regular_from_mont(const uint64_t* g1, uint64_t* reg8) {
     ec::big_store(reg8 + 4, y);
 }
 
+
+// ---- fft.Domain on the device -------------------------------------------------------------------------------------------------
+int domain_upload(gkrb200ec_ctx* c, uint32_t log_n) {
+    ec::NttDomainHost h;
+    if (!ec::ntt_domain_host(log_n, h)) return fail(GKRB200EC_ERR_ARG, "fft domain of 2^%u elements: at most 2^%d", log_n, ec::NTT_MAX_LOG);
+    const size_t n = (size_t)1 << log_n, half = n > 1 ? n / 2 : 1;
+    struct Piece {
+        uint64_t** dst;
+        const uint64_t* src;  // null: filled on the device
+        size_t words;
+    };
+    ec::NttDomainDev d{};
+    d.log_n = log_n;
+    const Piece pieces[] = {
+        {&d.tw, nullptr, 4 * half},
+        {&d.tw_inv, nullptr, 4 * half},
+        {&d.w_lo, h.w_lo.data(), h.w_lo.size()},
+        {&d.w_hi, h.w_hi.data(), h.w_hi.size()},
+        {&d.wi_lo, h.wi_lo.data(), h.wi_lo.size()},
+        {&d.wi_hi, h.wi_hi.data(), h.wi_hi.size()},
+        {&d.u_lo, h.u_lo.data(), h.u_lo.size()},
+        {&d.u_hi, h.u_hi.data(), h.u_hi.size()},
+        {&d.u_hi_n, h.u_hi_n.data(), h.u_hi_n.size()},
+        {&d.ui_lo, h.ui_lo.data(), h.ui_lo.size()},
+        {&d.ui_hi_n, h.ui_hi_n.data(), h.ui_hi_n.size()},
+        {&d.n_inv, h.n_inv, 4},
+        {&d.minus_two_inv, h.minus_two_inv, 4},
+    };
+    size_t total = 0;
+    for (const Piece& p : pieces) total += ec::msm_align(p.words * 8);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (c->dom_buf) CU_TRY(cudaFree(c->dom_buf));
+    c->dom_buf = nullptr;
+    c->have_domain = false;
+    CU_TRY(cudaMalloc((void**)&c->dom_buf, total));
+    size_t off = 0;
+    for (const Piece& p : pieces) {
+        *p.dst = (uint64_t*)(c->dom_buf + off);
+        if (p.src) {
+            CU_TRY(cudaMemcpyAsync(*p.dst, p.src, p.words * 8, cudaMemcpyHostToDevice, c->stream));
+            c->st.h2d_bytes += p.words * 8;
+        }
+        off += ec::msm_align(p.words * 8);
+    }
+    CudaExec ex{c->stream};
+    c->st.launches_total += (uint64_t)ec::ntt_domain_enqueue(ex, d);
+    if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "fft domain launch: %s", cudaGetErrorString(ex.err));
+    CU_TRY(cudaStreamSynchronize(c->stream));  // the host tables die with this frame
+    c->dom = d;
+    c->have_domain = true;
+    return 0;
+}
+int check_domain(gkrb200ec_ctx* c, size_t n) {
+    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
+    if (!c->have_domain) return fail(GKRB200EC_ERR_ARG, "no fft domain: call gkrb200ec_fft_domain_init first");
+    if (n != (size_t)1 << c->dom.log_n) return fail(GKRB200EC_ERR_ARG, "%zu elements for a domain of cardinality %zu", n, (size_t)1 << c->dom.log_n);
+    return 0;
+}
+int ensure_abc(gkrb200ec_ctx* c) {
+    void* p = c->d_abc;
+    const int rc = ensure(c, &p, &c->abc_cap, 3 * ((size_t)32 << c->dom.log_n));
+    c->d_abc = (uint64_t*)p;
+    return rc;
+}
+int run_fft(gkrb200ec_ctx* c, uint64_t* a, size_t n, int decimation, int coset, bool inverse) {
+    if (const int rc = check_domain(c, n)) return rc;
+    if (!a) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    if (decimation != GKRB200EC_DIT && decimation != GKRB200EC_DIF) return fail(GKRB200EC_ERR_ARG, "decimation %d", decimation);
+    if (coset != 0 && coset != 1) return fail(GKRB200EC_ERR_ARG, "coset %d: the domain has depth 1 (cosets 0 and 1)", coset);
+    CU_TRY(cudaSetDevice(c->device));
+    if (const int rc = ensure_abc(c)) return rc;
+    CU_TRY(cudaMemcpyAsync(c->d_abc, a, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CudaExec ex{c->stream};
+    CU_TRY(cudaEventRecord(c->e0, c->stream));
+    const int launches = ec::fft_enqueue(ex, c->dom, c->d_abc, decimation == GKRB200EC_DIF, coset, inverse);
+    CU_TRY(cudaEventRecord(c->e1, c->stream));
+    if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "fft launch: %s", cudaGetErrorString(ex.err));
+    CU_TRY(cudaMemcpyAsync(a, c->d_abc, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, c->e0, c->e1));
+    c->st.launches_total += (uint64_t)launches;
+    c->st.fft_calls++;
+    c->st.last_fft_device_ms = ms;
+    c->st.h2d_bytes += n * 32, c->st.d2h_bytes += n * 32;
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
 
-const char* gkrb200ec_version(void) { return "gkrb200ec 0.1 (sm_100a; G1 bucket method, XYZZ, signed digits)"; }
+const char* gkrb200ec_version(void) { return "gkrb200ec 0.2 (sm_100a; G1 bucket method in XYZZ with signed digits; radix-8 in-register Fr transforms)"; }
 const char* gkrb200ec_last_error(void) { return g_err; }
 
 int gkrb200ec_init(gkrb200ec_ctx** out, int device, void* stream) {
@@ -299,6 +394,8 @@ void gkrb200ec_free(gkrb200ec_ctx* c) {
     if (c->d_scalars) cudaFree(c->d_scalars);
     if (c->d_tmp_points) cudaFree(c->d_tmp_points);
     if (c->d_small) cudaFree(c->d_small);
+    if (c->dom_buf) cudaFree(c->dom_buf);
+    if (c->d_abc) cudaFree(c->d_abc);
     if (c->h_pin) cudaFreeHost(c->h_pin);
     if (c->e0) cudaEventDestroy(c->e0);
     if (c->e1) cudaEventDestroy(c->e1);
@@ -405,6 +502,52 @@ int gkrb200ec_derive_randomness_from_point(const uint64_t* g1, uint64_t* out) {
     uint64_t reg[8];
     regular_from_mont(g1, reg);
     derive_from_regular(reg, out);
+    return 0;
+}
+
+// ---- fft.Domain, FFT, FFTInverse, computeH ------------------------------------------------------------------------------------
+int gkrb200ec_fft_domain_init(gkrb200ec_ctx* c, uint64_t m) {
+    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
+    if (m == 0 || m > ((uint64_t)1 << ec::NTT_MAX_LOG)) return fail(GKRB200EC_ERR_ARG, "fft domain for %llu elements: 1 .. 2^%d", (unsigned long long)m, ec::NTT_MAX_LOG);
+    uint32_t log_n = 0;
+    while (((uint64_t)1 << log_n) < m) log_n++;  // ecc.NextPowerOfTwo
+    CU_TRY(cudaSetDevice(c->device));
+    return domain_upload(c, log_n);
+}
+uint64_t gkrb200ec_fft_domain_cardinality(gkrb200ec_ctx* c) { return (c && c->have_domain) ? (uint64_t)1 << c->dom.log_n : 0; }
+int gkrb200ec_fft(gkrb200ec_ctx* c, uint64_t* a, size_t n, int decimation, int coset) { return run_fft(c, a, n, decimation, coset, false); }
+int gkrb200ec_fft_inverse(gkrb200ec_ctx* c, uint64_t* a, size_t n, int decimation, int coset) { return run_fft(c, a, n, decimation, coset, true); }
+
+int gkrb200ec_compute_h(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, const uint64_t* cc, size_t n_in, uint64_t* h_out, const void** d_h_out) {
+    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
+    if (!c->have_domain) return fail(GKRB200EC_ERR_ARG, "no fft domain: call gkrb200ec_fft_domain_init first");
+    const size_t n = (size_t)1 << c->dom.log_n;
+    if (n_in > n) return fail(GKRB200EC_ERR_ARG, "%zu constraints for a domain of cardinality %zu", n_in, n);
+    if (n_in && (!a || !b || !cc)) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    if (!h_out && !d_h_out) return fail(GKRB200EC_ERR_ARG, "no output requested");
+    CU_TRY(cudaSetDevice(c->device));
+    if (const int rc = ensure_abc(c)) return rc;
+    uint64_t* v[3] = {c->d_abc, c->d_abc + 4 * n, c->d_abc + 8 * n};
+    const uint64_t* src[3] = {a, b, cc};
+    for (int t = 0; t < 3; t++) {  // append(a, padding...) (prove.go:319-323)
+        if (n_in) CU_TRY(cudaMemcpyAsync(v[t], src[t], n_in * 32, cudaMemcpyHostToDevice, c->stream));
+        if (n_in < n) CU_TRY(cudaMemsetAsync(v[t] + 4 * n_in, 0, (n - n_in) * 32, c->stream));
+    }
+    CudaExec ex{c->stream};
+    CU_TRY(cudaEventRecord(c->e0, c->stream));
+    const int launches = ec::compute_h_enqueue(ex, c->dom, v[0], v[1], v[2]);
+    CU_TRY(cudaEventRecord(c->e1, c->stream));
+    if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "computeH launch: %s", cudaGetErrorString(ex.err));
+    if (h_out) CU_TRY(cudaMemcpyAsync(h_out, v[0], n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, c->e0, c->e1));
+    c->st.launches_total += (uint64_t)launches;
+    c->st.fft_calls++;
+    c->st.last_fft_device_ms = ms;
+    c->st.h2d_bytes += 3 * n_in * 32;
+    if (h_out) c->st.d2h_bytes += n * 32;
+    if (d_h_out) *d_h_out = v[0];
     return 0;
 }
 

@@ -20,8 +20,8 @@
 //   7. k_window   one thread per window: sum of its chunks;  k_final: one thread: Horner over the windows (c doublings each),
 //                 affine conversion (one inversion), result in Montgomery and in regular form.
 // Every kernel is "one thread = one index", no shared memory and no intra-block cooperation: the bodies below are plain
-// functions of the index, launched through an executor (`Exec`).  The CUDA executor (msm.cu) runs them as grids of 128-thread
-// blocks; tests/emu/msm_emu.cpp runs the SAME bodies and the same driver loop by loop on the CPU against the oracle.  Entry
+// functions of the index, launched through an executor (`Exec`).  The CUDA executor (ec.cu) runs them as grids of 128-thread
+// blocks; tests/emu/ec_emu.cpp runs the SAME bodies and the same driver loop by loop on the CPU against the oracle.  Entry
 // order inside a bucket depends on the atomics and differs from run to run; the group sum, and therefore every output byte,
 // does not.
 #pragma once

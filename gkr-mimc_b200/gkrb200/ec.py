@@ -1,4 +1,4 @@
-"""Host-side mirror of the Groth16-side G1 operations of the gkr-mimc prover over libgkrb200ec.so.
+"""Host-side mirror of the Groth16-side operations of the gkr-mimc prover over libgkrb200ec.so.
 
     reference (Go)                                                        here
     --------------------------------------------------------------------  ---------------------------------------------
@@ -7,6 +7,9 @@
     G1Affine.Add (hints.go:184)                                            EcContext.Add(a, b)
     DeriveRandomnessFromPoint(g1) (hints.go:147-159)                       DeriveRandomnessFromPoint(g1)
     InitialRandomnessHint.Call (hints.go:162-192)                          EcContext.InitialRandomnessHint(...)
+    fft.NewDomain(m, 1, true) (groth16/setup.go:98)                        EcContext.NewDomain(m)
+    domain.FFT(a, fft.DIT|DIF, coset) / domain.FFTInverse                  EcContext.FFT(a, decimation, coset) / FFTInverse
+    computeH(a, b, c, &pk.Domain) (prove.go:310-366)                       EcContext.ComputeH(a, b, c) / ComputeHDevice
 
 Points are numpy uint64 arrays (..., 8) = []bn254.G1Affine (X, Y; Montgomery; infinity all zero), scalars (..., 4) = []fr.Element.
 Everything that touches a point array runs on the GPU; the library fails loudly without one.  There is no CPU fallback.
@@ -21,6 +24,7 @@ ROOT = os.path.dirname(_PKG)
 SO_PATH = os.path.join(ROOT, "libgkrb200ec.so")
 
 SCALARS_REGULAR, SCALARS_MONTGOMERY = 0, 1
+DIT, DIF = 0, 1  # fft.Decimation
 MAX_SLOTS = 16
 
 
@@ -37,6 +41,8 @@ class EcStats(ctypes.Structure):
         ("h2d_bytes", ctypes.c_uint64),
         ("d2h_bytes", ctypes.c_uint64),
         ("last_device_ms", ctypes.c_double),
+        ("fft_calls", ctypes.c_uint64),
+        ("last_fft_device_ms", ctypes.c_double),
     ]
 
 
@@ -73,6 +79,12 @@ def lib():
     L.gkrb200ec_keccak256.argtypes = [vp, sz, vp]
     L.gkrb200ec_derive_randomness_from_point.argtypes = [vp, vp]
     L.gkrb200ec_set_plan.argtypes = [vp, i32, i32]
+    L.gkrb200ec_fft_domain_init.argtypes = [vp, ctypes.c_uint64]
+    L.gkrb200ec_fft_domain_cardinality.argtypes = [vp]
+    L.gkrb200ec_fft_domain_cardinality.restype = ctypes.c_uint64
+    L.gkrb200ec_fft.argtypes = [vp, vp, sz, i32, i32]
+    L.gkrb200ec_fft_inverse.argtypes = [vp, vp, sz, i32, i32]
+    L.gkrb200ec_compute_h.argtypes = [vp, vp, vp, vp, sz, vp, ctypes.POINTER(vp)]
     L.gkrb200ec_get_stats.argtypes = [vp, ctypes.POINTER(EcStats)]
     _lib = L
     return L
@@ -192,6 +204,49 @@ class EcContext:
         check(lib().gkrb200ec_initial_randomness(self._h, slot_pub, _p(sp) if sp.shape[0] else None, sp.shape[0], slot_priv,
                                                  _p(sq) if sq.shape[0] else None, sq.shape[0], form, _p(krs_priv), _p(rnd)))
         return krs_priv, rnd
+
+    # ---- fft.Domain / computeH
+    def NewDomain(self, m):
+        """fft.NewDomain(m, 1, true): the context's resident domain; returns its cardinality"""
+        check(lib().gkrb200ec_fft_domain_init(self._h, int(m)))
+        return int(lib().gkrb200ec_fft_domain_cardinality(self._h))
+
+    @property
+    def Cardinality(self):
+        return int(lib().gkrb200ec_fft_domain_cardinality(self._h))
+
+    def FFT(self, a, decimation, coset=0):
+        """domain.FFT(a, decimation, coset) -> a new (n, 4) array (Go transforms in place)"""
+        a = fr_array(a).reshape(-1, 4).copy()
+        check(lib().gkrb200ec_fft(self._h, _p(a), a.shape[0], decimation, coset))
+        return a
+
+    def FFTInverse(self, a, decimation, coset=0):
+        a = fr_array(a).reshape(-1, 4).copy()
+        check(lib().gkrb200ec_fft_inverse(self._h, _p(a), a.shape[0], decimation, coset))
+        return a
+
+    def ComputeH(self, a, b, c):
+        """computeH(a, b, c, &pk.Domain) -> (cardinality, 4) REGULAR-form words, coefficients in bit-reversed order"""
+        a, b, c = (fr_array(v).reshape(-1, 4) for v in (a, b, c))
+        if not (a.shape == b.shape == c.shape):
+            raise ValueError("a, b, c must have the same length")
+        h = np.zeros((self.Cardinality, 4), dtype=np.uint64)
+        n_in = a.shape[0]
+        check(lib().gkrb200ec_compute_h(self._h, _p(a) if n_in else None, _p(b) if n_in else None, _p(c) if n_in else None, n_in, _p(h), None))
+        return h
+
+    def ComputeHDevice(self, a, b, c):
+        """the same, h left on the device: returns its raw device pointer (valid until the next FFT / ComputeH on this context),
+        ready for MultiExpDevice(slot_of_pk_G1_Z, ptr, cardinality, SCALARS_REGULAR) -- krs2 of prove.go:221"""
+        a, b, c = (fr_array(v).reshape(-1, 4) for v in (a, b, c))
+        if not (a.shape == b.shape == c.shape):
+            raise ValueError("a, b, c must have the same length")
+        ptr = ctypes.c_void_p()
+        n_in = a.shape[0]
+        check(lib().gkrb200ec_compute_h(self._h, _p(a) if n_in else None, _p(b) if n_in else None, _p(c) if n_in else None, n_in, None,
+                                        ctypes.byref(ptr)))
+        return ptr.value
 
     def set_plan(self, window_bits=0, task_size=0):
         check(lib().gkrb200ec_set_plan(self._h, window_bits, task_size))

@@ -1,11 +1,14 @@
-/* gkrb200_ec -- C ABI of the B200-native G1 multi-exponentiation (libgkrb200ec.so), SURVEY.md section 8(f4).
+/* gkrb200_ec -- C ABI of the B200-native Groth16-side operations (libgkrb200ec.so), SURVEY.md section 8(f4).
  *
- * The Groth16 side of Consensys/gkr-mimc's prover spends its time in bn254.G1Affine.MultiExp (gnark-crypto, reference go.mod:7):
+ * The Groth16 side of Consensys/gkr-mimc's prover spends its time in bn254.G1Affine.MultiExp and in the FFTs of computeH
+ * (gnark-crypto, reference go.mod:7):
  *   prover/gadget/hints.go:182-183   InitialRandomnessHint: the 3N GKR inputs/outputs against pubKGkr / privKGkrSigma
  *   prover/gadget/prove.go:76,91     KrsNotGkr / KrsPrivNotGkr
  *   prover/gadget/prove.go:189,202,221   Bs1, Ar, Krs2 (the G1 multi-exponentiations of ComputeGroth16Proof)
- * This library is that operation on the device, plus the rest of InitialRandomnessHint.Call (hints.go:147-192).  Each entry point
- * names the Go interface it replaces; the cgo binding is in INTEGRATION.md section 7.
+ *   prover/gadget/prove.go:310-366   computeH: seven FFTs over the constraint domain
+ * This library is those operations on the device, plus the rest of InitialRandomnessHint.Call (hints.go:147-192).  Each entry
+ * point names the Go interface it replaces; the cgo binding is in INTEGRATION.md section 7.  The G2 multi-exponentiation
+ * (prove.go:277) is not here.
  *
  * Data at the boundary is Go memory, unchanged:
  *   []bn254.G1Affine  = 8 x uint64 per point: X then Y, fp.Element = 4 little-endian limbs, Montgomery form (v * 2^256 mod p),
@@ -80,6 +83,31 @@ int gkrb200ec_g1_raw_bytes(const uint64_t *g1, uint8_t out[64]);
 int gkrb200ec_keccak256(const uint8_t *data, size_t len, uint8_t out[32]);
 int gkrb200ec_derive_randomness_from_point(const uint64_t *g1, uint64_t *randomness_out);
 
+/* ---- the FFT half of ComputeGroth16Proof (prover/gadget/prove.go:310-366 computeH) ------------------------------------------
+ * gnark-crypto ecc/bn254/fr/fft (reference go.mod:7): Domain, FFT, FFTInverse; DIT = 0, DIF = 1 as fft.Decimation.
+ *
+ * gkrb200ec_fft_domain_init:  fft.NewDomain(m, 1, true) as Groth16's setup builds it
+ *     (pkg/gnark/notinternal/backend/bn254/groth16/setup.go:98): cardinality = next power of two >= m (at most 2^26), Generator =
+ *     g^(2^(28 - log n)), FinerGenerator^2 = Generator; twiddle tables are built on the device and stay there.  Replaces the
+ *     context's previous domain.
+ * gkrb200ec_fft / gkrb200ec_fft_inverse:  domain.FFT(a, decimation, coset) / domain.FFTInverse(a, decimation, coset), in place on
+ *     a host slice of exactly `cardinality` Montgomery elements; coset 0 or 1.  DIF: natural input, bit-reversed output; DIT:
+ *     bit-reversed input, natural output -- no bit-reversal pass ever runs, as in the reference.
+ * gkrb200ec_compute_h:  h = computeH(a, b, c, &pk.Domain): a, b, c hold n_in <= cardinality Montgomery elements (the solved
+ *     L.w, R.w, O.w per constraint; zero padding is added on the device); h has `cardinality` elements in REGULAR form, coefficients
+ *     in bit-reversed order -- exactly what the reference passes to krs2.MultiExp(pk.G1.Z, h, ...) (prove.go:221; pk.G1.Z is
+ *     stored bit-reversed, setup.go:229).  h_out (host, may be NULL) receives a copy; d_h_out (may be NULL) receives the DEVICE
+ *     pointer of h, valid until the next FFT / computeH call on this context, ready for gkrb200ec_g1_multiexp_device(...,
+ *     GKRB200EC_SCALARS_REGULAR, ...): h never has to leave the GPU.                                                               */
+#define GKRB200EC_DIT 0
+#define GKRB200EC_DIF 1
+int gkrb200ec_fft_domain_init(gkrb200ec_ctx *ctx, uint64_t m);
+uint64_t gkrb200ec_fft_domain_cardinality(gkrb200ec_ctx *ctx);
+int gkrb200ec_fft(gkrb200ec_ctx *ctx, uint64_t *a, size_t n, int decimation, int coset);
+int gkrb200ec_fft_inverse(gkrb200ec_ctx *ctx, uint64_t *a, size_t n, int decimation, int coset);
+int gkrb200ec_compute_h(gkrb200ec_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_in, uint64_t *h_out,
+                        const void **d_h_out);
+
 /* Tuning / test hooks: force the window width c (2..16, 0 = cost model) and the accumulation task size (0 = twice the mean
  * bucket load).  The result never depends on them.                                                                             */
 int gkrb200ec_set_plan(gkrb200ec_ctx *ctx, int window_bits, int task_size);
@@ -92,6 +120,8 @@ typedef struct {
     uint64_t workspace_bytes;
     uint64_t h2d_bytes, d2h_bytes;
     double last_device_ms;     /* CUDA-event time of the last multi-exponentiation's kernels */
+    uint64_t fft_calls;        /* FFT / FFTInverse / computeH calls */
+    double last_fft_device_ms; /* CUDA-event time of the last FFT / FFTInverse / computeH's kernels */
 } gkrb200ec_stats;
 int gkrb200ec_get_stats(gkrb200ec_ctx *ctx, gkrb200ec_stats *out);
 

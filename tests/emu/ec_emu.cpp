@@ -1,16 +1,18 @@
-// CPU emulation of the multi-exponentiation kernels -- TEST INFRASTRUCTURE, never shipped or loaded by the product.
+// CPU emulation of the multi-exponentiation and FFT kernels -- TEST INFRASTRUCTURE, never shipped or loaded by the product.
 //
-// Compiles the product headers gkr-mimc_b200/csrc/ec/{field,g1,msm}.cuh with a plain C++ compiler: every kernel body is a function of
+// Compiles the product headers gkr-mimc_b200/csrc/ec/{field,g1,msm,ntt}.cuh with a plain C++ compiler: every kernel body is a function of
 // its thread index, and the executor below runs each "launch" as a loop.  Host-side, field.cuh's carry-chain primitives are plain
 // 64-bit C++ with the semantics of the inline-PTX ones the device uses (those are exercised on the GPU by every GKR parity test).
-// tests/test_msm_cpu.py drives this against the oracle, so the digit decomposition, counting sort, task splitting, XYZZ formulas
-// with all exceptional cases, window reduction and the driver's launch sequence are checked without a GPU; tests/test_zz_msm_gpu.py
-// then checks the real library on the device against the same oracle.
+// tests/test_msm_cpu.py and tests/test_ntt_cpu.py drive this against the oracles, so the digit decomposition, counting sort, task
+// splitting, XYZZ formulas with all exceptional cases, window reduction, the in-register butterfly passes, coset scalings and the
+// drivers' launch sequences are checked without a GPU; tests/test_zz_msm_gpu.py and tests/test_zz_ntt_gpu.py then check the real
+// library on the device against the same oracles.
 #include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "../../gkr-mimc_b200/csrc/ec/msm.cuh"
+#include "../../gkr-mimc_b200/csrc/ec/ntt.cuh"
 
 namespace {
 struct HostExec {
@@ -132,4 +134,76 @@ int emu_msm(const uint64_t* points, const uint64_t* scalars, size_t n, int scala
 }
 
 void emu_g1_add_affine(const uint64_t* a, const uint64_t* b, uint64_t* out16) { KAddAffine::run(0, a, b, out16); }
+}  // extern "C"
+
+// ---- FFT -----------------------------------------------------------------------------------------------------------------------
+namespace {
+struct EmuDomain {
+    ec::NttDomainHost h;
+    std::vector<uint64_t> tw, tw_inv;
+    ec::NttDomainDev d;
+};
+template <class Exec>
+bool emu_domain(Exec& ex, uint32_t log_n, EmuDomain& e) {
+    if (!ec::ntt_domain_host(log_n, e.h)) return false;
+    const size_t half = ((size_t)1 << log_n) / 2;
+    e.tw.assign(4 * (half ? half : 1), 0xA5A5A5A5A5A5A5A5ull);
+    e.tw_inv.assign(4 * (half ? half : 1), 0xA5A5A5A5A5A5A5A5ull);
+    e.d.log_n = log_n;
+    e.d.tw = e.tw.data(), e.d.tw_inv = e.tw_inv.data();
+    e.d.w_lo = e.h.w_lo.data(), e.d.w_hi = e.h.w_hi.data(), e.d.wi_lo = e.h.wi_lo.data(), e.d.wi_hi = e.h.wi_hi.data();
+    e.d.u_lo = e.h.u_lo.data(), e.d.u_hi = e.h.u_hi.data(), e.d.u_hi_n = e.h.u_hi_n.data();
+    e.d.ui_lo = e.h.ui_lo.data(), e.d.ui_hi_n = e.h.ui_hi_n.data();
+    e.d.n_inv = e.h.n_inv, e.d.minus_two_inv = e.h.minus_two_inv;
+    ec::ntt_domain_enqueue(ex, e.d);
+    return true;
+}
+}  // namespace
+
+extern "C" {
+// fft.Domain.FFT / FFTInverse in place on 2^log_n elements.  decimation: 0 DIT, 1 DIF; coset 0 / 1.  Returns launches, -1 on a bad size.
+int emu_fft(uint64_t* a, uint32_t log_n, int decimation, int coset, int inverse, int reverse) {
+    EmuDomain e;
+    if (reverse) {
+        HostExecReverse ex;
+        if (!emu_domain(ex, log_n, e)) return -1;
+        return ec::fft_enqueue(ex, e.d, a, decimation == 1, coset, inverse != 0);
+    }
+    HostExec ex;
+    if (!emu_domain(ex, log_n, e)) return -1;
+    return ec::fft_enqueue(ex, e.d, a, decimation == 1, coset, inverse != 0);
+}
+// computeH: a, b, c hold n_in elements; h_out 2^log_n elements (regular form, bit-reversed coefficient order)
+int emu_compute_h(const uint64_t* a, const uint64_t* b, const uint64_t* c, size_t n_in, uint32_t log_n, int reverse, uint64_t* h_out) {
+    const size_t n = (size_t)1 << log_n;
+    if (n_in > n) return -1;
+    std::vector<uint64_t> va(4 * n, 0), vb(4 * n, 0), vc(4 * n, 0);
+    memcpy(va.data(), a, 32 * n_in);
+    memcpy(vb.data(), b, 32 * n_in);
+    memcpy(vc.data(), c, 32 * n_in);
+    EmuDomain e;
+    int launches;
+    if (reverse) {
+        HostExecReverse ex;
+        if (!emu_domain(ex, log_n, e)) return -1;
+        launches = ec::compute_h_enqueue(ex, e.d, va.data(), vb.data(), vc.data());
+    } else {
+        HostExec ex;
+        if (!emu_domain(ex, log_n, e)) return -1;
+        launches = ec::compute_h_enqueue(ex, e.d, va.data(), vb.data(), vc.data());
+    }
+    memcpy(h_out, va.data(), 32 * n);
+    return launches;
+}
+// Domain constants as the product derives them: out[0..4) Generator, [4..8) FinerGenerator, [8..12) CardinalityInv, [12..16) (-2)^-1
+int emu_fft_domain(uint32_t log_n, uint64_t* out) {
+    ec::NttDomainHost h;
+    if (!ec::ntt_domain_host(log_n, h)) return -1;
+    memcpy(out, h.generator, 32);
+    memcpy(out + 4, h.finer_generator, 32);
+    memcpy(out + 8, h.n_inv, 32);
+    memcpy(out + 12, h.minus_two_inv, 32);
+    return 0;
+}
+uint32_t emu_ntt_rev(uint32_t x, uint32_t log_n) { return ec::ntt_rev(x, log_n); }
 }

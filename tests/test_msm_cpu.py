@@ -5,7 +5,7 @@ Three layers, none of which needs a GPU:
      double-and-add in Jacobian coordinates) agrees with the independent Python big-integer one (oracle/pyref_msm.py);
   2. the product's kernel bodies (gkr-mimc_b200/csrc/ec/*.cuh: field arithmetic, XYZZ group law with every exceptional case, digit
      decomposition, counting sort, task splitting, bucket / chunk / window reduction, the launch sequence of msm_enqueue) are
-     compiled for the host by tests/emu/msm_emu.cpp and compared with the oracle -- each "launch" run as a loop, forwards and
+     compiled for the host by tests/emu/ec_emu.cpp and compared with the oracle -- each "launch" run as a loop, forwards and
      backwards; on the host the carry chains are plain C++, on the device they are the inline-PTX primitives of fr_device.cuh;
   3. libgkrb200ec.so loads, exports every symbol include/gkrb200_ec.h declares, its host-only entry points (RawBytes, legacy
      Keccak-256, DeriveRandomnessFromPoint) agree with the oracle, and the device entry points fail loudly without a GPU.
@@ -21,8 +21,8 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EMU_SRC = os.path.join(ROOT, "tests", "emu", "msm_emu.cpp")
-EMU_SO = os.path.join(ROOT, "tests", "emu", "_build", "libmsmemu.so")
+EMU_SRC = os.path.join(ROOT, "tests", "emu", "ec_emu.cpp")
+EMU_SO = os.path.join(ROOT, "tests", "emu", "_build", "libecemu.so")
 EC_DIR = os.path.join(ROOT, "gkr-mimc_b200", "csrc", "ec")
 
 
