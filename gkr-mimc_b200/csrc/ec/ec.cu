@@ -64,11 +64,12 @@ struct gkrb200ec_ctx {
     size_t sc_cap = 0;
     uint64_t* d_tmp_points = nullptr;  // staging for one-shot host points
     size_t tp_cap = 0;
-    uint64_t* d_small = nullptr;  // 2 input points + 16 result words for gkrb200ec_g1_add
-    uint64_t* h_pin = nullptr;    // pinned: 16 result words + error flag
+    uint64_t* d_small = nullptr;  // 2 input points + the result (Montgomery, regular) of gkrb200ec_g1_add / g2_add: 4 x 16 words at most
+    uint64_t* h_pin = nullptr;    // pinned: up to 32 result words; the error flag at word PIN_FLAG
     struct Slot {
         uint64_t* d = nullptr;
         size_t n = 0;
+        int words = 0;  // u64 words per point: 8 = G1Affine, 16 = G2Affine
     } slots[GKRB200EC_MAX_SLOTS];
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int c_force = 0, T_force = 0;
@@ -83,6 +84,8 @@ struct gkrb200ec_ctx {
 
 namespace {
 
+constexpr int PIN_FLAG = 48;  // word index of the error flag in h_pin (64 words)
+
 int ensure(gkrb200ec_ctx* c, void** p, size_t* cap, size_t bytes) {
     if (*cap >= bytes) return 0;
     if (*p) CU_TRY(cudaFree(*p));
@@ -94,15 +97,17 @@ int ensure(gkrb200ec_ctx* c, void** p, size_t* cap, size_t bytes) {
     return 0;
 }
 
-// out16: affine result, Montgomery (8 words) then regular form (8 words)
-int run_msm(gkrb200ec_ctx* c, const uint64_t* d_points, const uint64_t* d_scalars, size_t n, int form, uint64_t* out16) {
+// out: affine result, Montgomery (C::AFF_WORDS words) then regular form (C::AFF_WORDS words)
+template <class C>
+int run_msm(gkrb200ec_ctx* c, const uint64_t* d_points, const uint64_t* d_scalars, size_t n, int form, uint64_t* out) {
+    constexpr size_t RES = 2 * C::AFF_WORDS;
     if (n == 0) {
-        memset(out16, 0, 16 * sizeof(uint64_t));
+        memset(out, 0, RES * sizeof(uint64_t));
         return 0;
     }
     const ec::MsmPlan pl = ec::msm_make_plan(n, form == GKRB200EC_SCALARS_MONTGOMERY, c->c_force, c->T_force);
     if ((uint64_t)pl.n * pl.W >= 0xffffffffull) return fail(GKRB200EC_ERR_ARG, "multiexp: %zu points x %u windows does not fit 32-bit entry offsets", n, pl.W);
-    const ec::MsmWorkspace ws = ec::msm_layout(pl);
+    const ec::MsmWorkspace ws = ec::msm_layout(pl, 8 * C::X_WORDS, 8 * C::AFF_WORDS);
     {
         void* p = c->ws;
         const int rc = ensure(c, &p, &c->ws_bytes, ws.bytes);
@@ -111,11 +116,11 @@ int run_msm(gkrb200ec_ctx* c, const uint64_t* d_points, const uint64_t* d_scalar
     }
     CudaExec ex{c->stream};
     CU_TRY(cudaEventRecord(c->e0, c->stream));
-    const int launches = ec::msm_enqueue(ex, pl, ws, c->ws, d_points, d_scalars);
+    const int launches = ec::msm_enqueue<C>(ex, pl, ws, c->ws, d_points, d_scalars);
     CU_TRY(cudaEventRecord(c->e1, c->stream));
     if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "multiexp launch: %s", cudaGetErrorString(ex.err));
-    CU_TRY(cudaMemcpyAsync(c->h_pin, c->ws + ws.out, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(cudaMemcpyAsync(c->h_pin + 16, c->ws + ws.err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->h_pin, c->ws + ws.out, RES * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->h_pin + PIN_FLAG, c->ws + ws.err, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     CU_TRY(cudaEventElapsedTime(&ms, c->e0, c->e1));
@@ -124,12 +129,12 @@ int run_msm(gkrb200ec_ctx* c, const uint64_t* d_points, const uint64_t* d_scalar
     c->st.last_n = pl.n, c->st.last_c = pl.c, c->st.last_windows = pl.W, c->st.last_task_size = pl.T;
     c->st.last_tasks_max = pl.max_tasks;
     c->st.workspace_bytes = c->ws_bytes;
-    c->st.d2h_bytes += 16 * sizeof(uint64_t) + sizeof(uint32_t);
+    c->st.d2h_bytes += RES * sizeof(uint64_t) + sizeof(uint32_t);
     c->st.last_device_ms = ms;
-    const uint32_t flag = (uint32_t)c->h_pin[16];
+    const uint32_t flag = (uint32_t)c->h_pin[PIN_FLAG];
     if (flag & ec::MSM_ERR_SCALAR_RANGE) return fail(GKRB200EC_ERR_ARG, "multiexp: a regular-form scalar is not reduced (>= q)");
     if (flag) return fail(GKRB200EC_ERR_CUDA, "multiexp: internal digit overflow (flag %u)", flag);
-    memcpy(out16, c->h_pin, 16 * sizeof(uint64_t));
+    memcpy(out, c->h_pin, RES * sizeof(uint64_t));
     return 0;
 }
 
@@ -143,23 +148,90 @@ int stage_scalars(gkrb200ec_ctx* c, const uint64_t* scalars, size_t n) {
     return 0;
 }
 
-int check_slot(gkrb200ec_ctx* c, int slot, size_t n) {
+int check_slot(gkrb200ec_ctx* c, int slot, size_t n, int words) {
     if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
     if (slot < 0 || slot >= GKRB200EC_MAX_SLOTS) return fail(GKRB200EC_ERR_ARG, "base slot %d out of range", slot);
     if (n > c->slots[slot].n) return fail(GKRB200EC_ERR_ARG, "%zu scalars for %zu bases in slot %d", n, c->slots[slot].n, slot);
+    if (n && c->slots[slot].words != words) return fail(GKRB200EC_ERR_ARG, "slot %d holds %s points", slot, c->slots[slot].words == 8 ? "G1" : "G2");
     return 0;
 }
 
-int add_points(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out16) {
-    CU_TRY(cudaMemcpyAsync(c->d_small, a, 64, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaMemcpyAsync(c->d_small + 8, b, 64, cudaMemcpyHostToDevice, c->stream));
+// out: a + b, Montgomery then regular form (2 * C::AFF_WORDS words)
+template <class C>
+int add_points(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    constexpr size_t AW = C::AFF_WORDS;
+    CU_TRY(cudaMemcpyAsync(c->d_small, a, AW * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaMemcpyAsync(c->d_small + AW, b, AW * 8, cudaMemcpyHostToDevice, c->stream));
     CudaExec ex{c->stream};
-    c->st.launches_total += (uint64_t)ex.launch<ec::KAddAffine>(1, (const uint64_t*)c->d_small, (const uint64_t*)(c->d_small + 8), c->d_small + 16);
-    if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "g1 add launch: %s", cudaGetErrorString(ex.err));
-    CU_TRY(cudaMemcpyAsync(c->h_pin, c->d_small + 16, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    c->st.launches_total += (uint64_t)ex.launch<ec::KAddAffine<C>>(1, (const uint64_t*)c->d_small, (const uint64_t*)(c->d_small + AW), c->d_small + 2 * AW);
+    if (ex.err != cudaSuccess) return fail(GKRB200EC_ERR_CUDA, "point addition launch: %s", cudaGetErrorString(ex.err));
+    CU_TRY(cudaMemcpyAsync(c->h_pin, c->d_small + 2 * AW, 2 * AW * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
-    memcpy(out16, c->h_pin, 16 * sizeof(uint64_t));
-    c->st.h2d_bytes += 128, c->st.d2h_bytes += 128;
+    memcpy(out, c->h_pin, 2 * AW * 8);
+    c->st.h2d_bytes += 2 * AW * 8, c->st.d2h_bytes += 2 * AW * 8;
+    return 0;
+}
+
+int set_bases(gkrb200ec_ctx* c, int slot, const uint64_t* points, size_t n, int words) {
+    if (const int rc = check_slot(c, slot, 0, words)) return rc;
+    if (n && !points) return fail(GKRB200EC_ERR_ARG, "null points");
+    if (n > GKRB200EC_MAX_POINTS) return fail(GKRB200EC_ERR_ARG, "%zu points: at most %u", n, GKRB200EC_MAX_POINTS);
+    CU_TRY(cudaSetDevice(c->device));
+    auto& s = c->slots[slot];
+    if (s.d) {
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        CU_TRY(cudaFree(s.d));
+        s.d = nullptr, s.n = 0, s.words = 0;
+    }
+    if (n == 0) return 0;
+    CU_TRY(cudaMalloc((void**)&s.d, n * words * 8));
+    CU_TRY(cudaMemcpyAsync(s.d, points, n * words * 8, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    s.n = n, s.words = words;
+    c->st.h2d_bytes += n * words * 8;
+    return 0;
+}
+
+// the three host-facing forms of MultiExp, once per curve
+template <class C>
+int multiexp_device(gkrb200ec_ctx* c, int slot, const void* d_scalars, size_t n, int form, uint64_t* out) {
+    if (const int rc = check_slot(c, slot, n, C::AFF_WORDS)) return rc;
+    if (!out || (n && !d_scalars)) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    if (form != GKRB200EC_SCALARS_REGULAR && form != GKRB200EC_SCALARS_MONTGOMERY) return fail(GKRB200EC_ERR_ARG, "scalar form %d", form);
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t r[2 * C::AFF_WORDS];
+    if (const int rc = run_msm<C>(c, c->slots[slot].d, (const uint64_t*)d_scalars, n, form, r)) return rc;
+    memcpy(out, r, C::AFF_WORDS * 8);
+    return 0;
+}
+template <class C>
+int multiexp_host(gkrb200ec_ctx* c, int slot, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
+    if (const int rc = check_slot(c, slot, n, C::AFF_WORDS)) return rc;
+    if (!out || (n && !scalars)) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    CU_TRY(cudaSetDevice(c->device));
+    if (n)
+        if (const int rc = stage_scalars(c, scalars, n)) return rc;
+    return multiexp_device<C>(c, slot, c->d_scalars, n, form, out);
+}
+template <class C>
+int multiexp_points(gkrb200ec_ctx* c, const uint64_t* points, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
+    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
+    if (!out || (n && (!points || !scalars))) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    if (n > GKRB200EC_MAX_POINTS) return fail(GKRB200EC_ERR_ARG, "%zu points: at most %u", n, GKRB200EC_MAX_POINTS);
+    if (form != GKRB200EC_SCALARS_REGULAR && form != GKRB200EC_SCALARS_MONTGOMERY) return fail(GKRB200EC_ERR_ARG, "scalar form %d", form);
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t r[2 * C::AFF_WORDS];
+    if (n) {
+        void* p = c->d_tmp_points;
+        const int rc = ensure(c, &p, &c->tp_cap, n * C::AFF_WORDS * 8);
+        c->d_tmp_points = (uint64_t*)p;
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(c->d_tmp_points, points, n * C::AFF_WORDS * 8, cudaMemcpyHostToDevice, c->stream));
+        c->st.h2d_bytes += n * C::AFF_WORDS * 8;
+        if (const int rc2 = stage_scalars(c, scalars, n)) return rc2;
+    }
+    if (const int rc = run_msm<C>(c, c->d_tmp_points, c->d_scalars, n, form, r)) return rc;
+    memcpy(out, r, C::AFF_WORDS * 8);
     return 0;
 }
 
@@ -372,8 +444,8 @@ int gkrb200ec_init(gkrb200ec_ctx** out, int device, void* stream) {
         step(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "stream");
         c->own_stream = rc == 0;
     }
-    step(cudaMalloc((void**)&c->d_small, 32 * sizeof(uint64_t)), "scratch");
-    step(cudaMallocHost((void**)&c->h_pin, 32 * sizeof(uint64_t)), "pinned result");
+    step(cudaMalloc((void**)&c->d_small, 64 * sizeof(uint64_t)), "scratch");
+    step(cudaMallocHost((void**)&c->h_pin, 64 * sizeof(uint64_t)), "pinned result");
     step(cudaEventCreate(&c->e0), "event");
     step(cudaEventCreate(&c->e1), "event");
     if (rc) {
@@ -403,73 +475,42 @@ void gkrb200ec_free(gkrb200ec_ctx* c) {
     delete c;
 }
 
-int gkrb200ec_g1_set_bases(gkrb200ec_ctx* c, int slot, const uint64_t* points, size_t n) {
-    if (const int rc = check_slot(c, slot, 0)) return rc;
-    if (n && !points) return fail(GKRB200EC_ERR_ARG, "null points");
-    if (n > GKRB200EC_MAX_POINTS) return fail(GKRB200EC_ERR_ARG, "%zu points: at most %u", n, GKRB200EC_MAX_POINTS);
-    CU_TRY(cudaSetDevice(c->device));
-    auto& s = c->slots[slot];
-    if (s.d) {
-        CU_TRY(cudaStreamSynchronize(c->stream));
-        CU_TRY(cudaFree(s.d));
-        s.d = nullptr, s.n = 0;
-    }
-    if (n == 0) return 0;
-    CU_TRY(cudaMalloc((void**)&s.d, n * 64));
-    CU_TRY(cudaMemcpyAsync(s.d, points, n * 64, cudaMemcpyHostToDevice, c->stream));
-    CU_TRY(cudaStreamSynchronize(c->stream));
-    s.n = n;
-    c->st.h2d_bytes += n * 64;
-    return 0;
-}
+int gkrb200ec_g1_set_bases(gkrb200ec_ctx* c, int slot, const uint64_t* points, size_t n) { return set_bases(c, slot, points, n, ec::G1::AFF_WORDS); }
+int gkrb200ec_g2_set_bases(gkrb200ec_ctx* c, int slot, const uint64_t* points, size_t n) { return set_bases(c, slot, points, n, ec::G2::AFF_WORDS); }
 
 int gkrb200ec_g1_multiexp_device(gkrb200ec_ctx* c, int slot, const void* d_scalars, size_t n, int form, uint64_t* out) {
-    if (const int rc = check_slot(c, slot, n)) return rc;
-    if (!out || (n && !d_scalars)) return fail(GKRB200EC_ERR_ARG, "null pointer");
-    if (form != GKRB200EC_SCALARS_REGULAR && form != GKRB200EC_SCALARS_MONTGOMERY) return fail(GKRB200EC_ERR_ARG, "scalar form %d", form);
-    CU_TRY(cudaSetDevice(c->device));
-    uint64_t r[16];
-    if (const int rc = run_msm(c, c->slots[slot].d, (const uint64_t*)d_scalars, n, form, r)) return rc;
-    memcpy(out, r, 64);
-    return 0;
+    return multiexp_device<ec::G1>(c, slot, d_scalars, n, form, out);
 }
-
 int gkrb200ec_g1_multiexp(gkrb200ec_ctx* c, int slot, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
-    if (const int rc = check_slot(c, slot, n)) return rc;
-    if (!out || (n && !scalars)) return fail(GKRB200EC_ERR_ARG, "null pointer");
-    CU_TRY(cudaSetDevice(c->device));
-    if (n)
-        if (const int rc = stage_scalars(c, scalars, n)) return rc;
-    return gkrb200ec_g1_multiexp_device(c, slot, c->d_scalars, n, form, out);
+    return multiexp_host<ec::G1>(c, slot, scalars, n, form, out);
 }
-
 int gkrb200ec_g1_multiexp_points(gkrb200ec_ctx* c, const uint64_t* points, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
-    if (!c) return fail(GKRB200EC_ERR_ARG, "null context");
-    if (!out || (n && (!points || !scalars))) return fail(GKRB200EC_ERR_ARG, "null pointer");
-    if (n > GKRB200EC_MAX_POINTS) return fail(GKRB200EC_ERR_ARG, "%zu points: at most %u", n, GKRB200EC_MAX_POINTS);
-    if (form != GKRB200EC_SCALARS_REGULAR && form != GKRB200EC_SCALARS_MONTGOMERY) return fail(GKRB200EC_ERR_ARG, "scalar form %d", form);
-    CU_TRY(cudaSetDevice(c->device));
-    uint64_t r[16];
-    if (n) {
-        void* p = c->d_tmp_points;
-        const int rc = ensure(c, &p, &c->tp_cap, n * 64);
-        c->d_tmp_points = (uint64_t*)p;
-        if (rc) return rc;
-        CU_TRY(cudaMemcpyAsync(c->d_tmp_points, points, n * 64, cudaMemcpyHostToDevice, c->stream));
-        c->st.h2d_bytes += n * 64;
-        if (const int rc2 = stage_scalars(c, scalars, n)) return rc2;
-    }
-    if (const int rc = run_msm(c, c->d_tmp_points, c->d_scalars, n, form, r)) return rc;
-    memcpy(out, r, 64);
-    return 0;
+    return multiexp_points<ec::G1>(c, points, scalars, n, form, out);
+}
+int gkrb200ec_g2_multiexp_device(gkrb200ec_ctx* c, int slot, const void* d_scalars, size_t n, int form, uint64_t* out) {
+    return multiexp_device<ec::G2>(c, slot, d_scalars, n, form, out);
+}
+int gkrb200ec_g2_multiexp(gkrb200ec_ctx* c, int slot, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
+    return multiexp_host<ec::G2>(c, slot, scalars, n, form, out);
+}
+int gkrb200ec_g2_multiexp_points(gkrb200ec_ctx* c, const uint64_t* points, const uint64_t* scalars, size_t n, int form, uint64_t* out) {
+    return multiexp_points<ec::G2>(c, points, scalars, n, form, out);
 }
 
 int gkrb200ec_g1_add(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out) {
     if (!c || !a || !b || !out) return fail(GKRB200EC_ERR_ARG, "null pointer");
     CU_TRY(cudaSetDevice(c->device));
-    uint64_t r[16];
-    if (const int rc = add_points(c, a, b, r)) return rc;
-    memcpy(out, r, 64);
+    uint64_t r[2 * ec::G1::AFF_WORDS];
+    if (const int rc = add_points<ec::G1>(c, a, b, r)) return rc;
+    memcpy(out, r, ec::G1::AFF_WORDS * 8);
+    return 0;
+}
+int gkrb200ec_g2_add(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    if (!c || !a || !b || !out) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    CU_TRY(cudaSetDevice(c->device));
+    uint64_t r[2 * ec::G2::AFF_WORDS];
+    if (const int rc = add_points<ec::G2>(c, a, b, r)) return rc;
+    memcpy(out, r, ec::G2::AFF_WORDS * 8);
     return 0;
 }
 
@@ -479,7 +520,7 @@ int gkrb200ec_initial_randomness(gkrb200ec_ctx* c, int slot_pub, const uint64_t*
     uint64_t krs[8], priv[8], sum[16];
     if (const int rc = gkrb200ec_g1_multiexp(c, slot_pub, scalars_pub, n_pub, form, krs)) return rc;        // hints.go:182
     if (const int rc = gkrb200ec_g1_multiexp(c, slot_priv, scalars_priv, n_priv, form, priv)) return rc;     // hints.go:183
-    if (const int rc = add_points(c, krs, priv, sum)) return rc;                                             // hints.go:184
+    if (const int rc = add_points<ec::G1>(c, krs, priv, sum)) return rc;                                             // hints.go:184
     memcpy(krs_gkr_priv_out, priv, 64);                                                                      // hints.go:186
     derive_from_regular(sum + 8, initial_randomness_out);                                                    // hints.go:188-189
     return 0;

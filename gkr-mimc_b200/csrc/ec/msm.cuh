@@ -1,8 +1,10 @@
-// G1Affine.MultiExp on the device: the bucket method (Pippenger) laid out for a GPU.
+// G1Affine.MultiExp and G2Affine.MultiExp on the device: the bucket method (Pippenger) laid out for a GPU, written once over the
+// curve (curve.cuh: G1 over Fp, G2 over Fp2).
 //
-// Replaces gnark-crypto's ecc/bn254 G1Affine.MultiExp (reference go.mod:7, un-vendored; a goroutine per window, each walking
-// all scalars) behind its call sites prover/gadget/hints.go:182-183 (InitialRandomnessHint: the 3N GKR inputs/outputs against
-// pubKGkr / privKGkrSigma) and prover/gadget/prove.go:76,91,189,202,221.  result = sum_i scalars[i] * points[i].
+// Replaces gnark-crypto's ecc/bn254 G1Affine.MultiExp / G2Affine.MultiExp (reference go.mod:7, un-vendored; a goroutine per
+// window, each walking all scalars) behind their call sites prover/gadget/hints.go:182-183 (InitialRandomnessHint: the 3N GKR
+// inputs/outputs against pubKGkr / privKGkrSigma), prover/gadget/prove.go:76,91,189,202,221 (G1) and prove.go:277 (G2, Bs).
+// result = sum_i scalars[i] * points[i].
 //
 // Plan (all sizes from `MsmPlan`): scalars are cut into W signed c-bit digits d in [-2^(c-1), 2^(c-1)]; a non-zero digit sends
 // +-point i to bucket |d| - 1 of window w.  Instead of W passes over the input with per-window bucket arrays, every (window,
@@ -25,7 +27,7 @@
 // order inside a bucket depends on the atomics and differs from run to run; the group sum, and therefore every output byte,
 // does not.
 #pragma once
-#include "g1.cuh"
+#include "curve.cuh"
 
 namespace ec {
 
@@ -187,9 +189,11 @@ struct KScanC {  // j < nch
         if (j + 1 == nch) out[n] = part[nch];
     }
 };
+template <class C>
 struct KAccum {  // t < max_tasks
     static EC_HD void run(size_t t, MsmPlan pl, const uint64_t* points, const uint32_t* entries, const uint32_t* off, const uint32_t* count,
-                          const uint32_t* toff, G1XRaw* partial) {
+                          const uint32_t* toff, uint64_t* partial) {
+        typedef typename C::MInline M;
         if (t >= toff[pl.nkeys]) return;
         uint32_t lo = 0, hi = pl.nkeys;  // largest key with toff[key] <= t
         while (hi - lo > 1) {
@@ -201,77 +205,89 @@ struct KAccum {  // t < max_tasks
         const size_t first = (size_t)off[key] + (t - toff[key]) * (size_t)pl.T;
         const size_t end_key = (size_t)off[key] + count[key];
         const size_t last = first + pl.T < end_key ? first + pl.T : end_key;
-        G1X acc = g1x_inf();
+        typename C::X acc = C::x_inf();
         // the next point is requested before the current addition starts (one gather latency hidden per iteration)
         uint32_t e_cur = entries[first];
-        G1Affine p_cur = g1_aff_load(points + 8 * (size_t)(e_cur & 0x7fffffffu));
+        typename C::Affine p_cur = C::aff_load(points + (size_t)C::AFF_WORDS * (e_cur & 0x7fffffffu));
         for (size_t e = first; e < last; e++) {
             uint32_t e_nxt = 0;
-            G1Affine p_nxt = p_cur;
+            typename C::Affine p_nxt = p_cur;
             if (e + 1 < last) {
                 e_nxt = entries[e + 1];
-                p_nxt = g1_aff_load(points + 8 * (size_t)(e_nxt & 0x7fffffffu));
+                p_nxt = C::aff_load(points + (size_t)C::AFF_WORDS * (e_nxt & 0x7fffffffu));
             }
-            if ((e_cur & 0x80000000u) && !g1_aff_is_inf(p_cur)) p_cur.y = f_neg<Fp>(p_cur.y);
-            acc = g1x_add_affine<MulInline>(acc, p_cur);
+            if (e_cur & 0x80000000u) p_cur = C::aff_neg(p_cur);
+            acc = C::template add_affine<M>(acc, p_cur);
             e_cur = e_nxt;
             p_cur = p_nxt;
         }
-        g1x_store(partial + t, acc);
+        C::x_store(partial + (size_t)C::X_WORDS * t, acc);
     }
 };
+template <class C>
 struct KBucket {  // k < nkeys
-    static EC_HD void run(size_t k, const uint32_t* toff, const G1XRaw* partial, G1XRaw* bucket) {
+    static EC_HD void run(size_t k, const uint32_t* toff, const uint64_t* partial, uint64_t* bucket) {
+        typedef typename C::MCall M;
         const uint32_t lo = toff[k], hi = toff[k + 1];
-        G1X acc = g1x_inf();
-        if (hi > lo) acc = g1x_load(partial + lo);
-        for (uint32_t t = lo + 1; t < hi; t++) acc = g1x_add<MulCall>(acc, g1x_load(partial + t));
-        g1x_store(bucket + k, acc);
+        typename C::X acc = C::x_inf();
+        if (hi > lo) acc = C::x_load(partial + (size_t)C::X_WORDS * lo);
+        for (uint32_t t = lo + 1; t < hi; t++) acc = C::template add<M>(acc, C::x_load(partial + (size_t)C::X_WORDS * t));
+        C::x_store(bucket + (size_t)C::X_WORDS * k, acc);
     }
 };
+template <class C>
 struct KChunk {  // j < W * nchunks
-    static EC_HD void run(size_t j, MsmPlan pl, const G1XRaw* bucket, G1XRaw* chunk_out) {
+    static EC_HD void run(size_t j, MsmPlan pl, const uint64_t* bucket, uint64_t* chunk_out) {
+        typedef typename C::MCall M;
         const uint32_t w = (uint32_t)(j / pl.nchunks), ci = (uint32_t)(j % pl.nchunks);
         const uint32_t lo = ci * pl.L, hi = lo + pl.L < pl.B ? lo + pl.L : pl.B;
-        G1X run = g1x_inf(), acc = g1x_inf();
+        typename C::X run = C::x_inf(), acc = C::x_inf();
         for (uint32_t b = hi; b-- > lo;) {
-            run = g1x_add<MulCall>(run, g1x_load(bucket + (size_t)w * pl.B + b));
-            acc = g1x_add<MulCall>(acc, run);
+            run = C::template add<M>(run, C::x_load(bucket + (size_t)C::X_WORDS * ((size_t)w * pl.B + b)));
+            acc = C::template add<M>(acc, run);
         }
         // acc = sum (b - lo + 1) S_b; bucket b weighs b + 1
-        if (lo) acc = g1x_add<MulCall>(acc, g1x_mul_small<MulCall>(run, lo));
-        g1x_store(chunk_out + j, acc);
+        if (lo) acc = C::template add<M>(acc, C::template mul_small<M>(run, lo));
+        C::x_store(chunk_out + (size_t)C::X_WORDS * j, acc);
     }
 };
+template <class C>
 struct KWindow {  // w < W
-    static EC_HD void run(size_t w, MsmPlan pl, const G1XRaw* chunk_out, G1XRaw* win) {
-        G1X acc = g1x_inf();
-        for (uint32_t ci = 0; ci < pl.nchunks; ci++) acc = g1x_add<MulCall>(acc, g1x_load(chunk_out + w * pl.nchunks + ci));
-        g1x_store(win + w, acc);
+    static EC_HD void run(size_t w, MsmPlan pl, const uint64_t* chunk_out, uint64_t* win) {
+        typedef typename C::MCall M;
+        typename C::X acc = C::x_inf();
+        for (uint32_t ci = 0; ci < pl.nchunks; ci++) acc = C::template add<M>(acc, C::x_load(chunk_out + (size_t)C::X_WORDS * (w * pl.nchunks + ci)));
+        C::x_store(win + (size_t)C::X_WORDS * w, acc);
     }
 };
-// out[0..8): affine result, Montgomery (G1Affine memory image); out[8..16): the same in regular form (for RawBytes)
-EC_HD void msm_store_result(uint64_t* out, const G1X& r) {
-    const G1Affine a = g1x_to_affine(r);
-    g1_aff_store(out, a);
-    G1Affine reg;
-    reg.x = f_from_mont<Fp>(a.x), reg.y = f_from_mont<Fp>(a.y);
-    g1_aff_store(out + 8, reg);
+// out[0 .. AFF_WORDS): affine result, Montgomery (the G1Affine / G2Affine memory image); out[AFF_WORDS .. 2 AFF_WORDS): the same in
+// regular form (for RawBytes)
+template <class C>
+EC_HD void msm_store_result(uint64_t* out, const typename C::X& r) {
+    const typename C::Affine a = C::to_affine(r);
+    C::aff_store(out, a);
+    typename C::Affine reg;
+    reg.x = C::Field::from_mont(a.x), reg.y = C::Field::from_mont(a.y);
+    C::aff_store(out + C::AFF_WORDS, reg);
 }
+template <class C>
 struct KFinal {  // one thread
-    static EC_HD void run(size_t, MsmPlan pl, const G1XRaw* win, uint64_t* out) {
-        G1X acc = g1x_inf();
+    static EC_HD void run(size_t, MsmPlan pl, const uint64_t* win, uint64_t* out) {
+        typedef typename C::MCall M;
+        typename C::X acc = C::x_inf();
         for (uint32_t w = pl.W; w-- > 0;) {
-            for (uint32_t k = 0; k < pl.c; k++) acc = g1x_dbl<MulCall>(acc);
-            acc = g1x_add<MulCall>(acc, g1x_load(win + w));
+            for (uint32_t k = 0; k < pl.c; k++) acc = C::template dbl<M>(acc);
+            acc = C::template add<M>(acc, C::x_load(win + (size_t)C::X_WORDS * w));
         }
-        msm_store_result(out, acc);
+        msm_store_result<C>(out, acc);
     }
 };
+template <class C>
 struct KAddAffine {  // one thread: out = a + b (G1Affine.Add, hints.go:184), same output format as KFinal
     static EC_HD void run(size_t, const uint64_t* a, const uint64_t* b, uint64_t* out) {
-        const G1X s = g1x_add_affine<MulCall>(g1x_from_affine(g1_aff_load(a)), g1_aff_load(b));
-        msm_store_result(out, s);
+        typedef typename C::MCall M;
+        const typename C::X s = C::template add_affine<M>(C::from_affine(C::aff_load(a)), C::aff_load(b));
+        msm_store_result<C>(out, s);
     }
 };
 
@@ -280,7 +296,7 @@ struct MsmWorkspace {  // offsets into one device buffer
     size_t count, off, cursor, tcount, toff, part, entries, partial, bucket, chunk_out, win, err, out, bytes;
 };
 inline size_t msm_align(size_t x) { return (x + 255) & ~(size_t)255; }
-inline MsmWorkspace msm_layout(const MsmPlan& pl) {
+inline MsmWorkspace msm_layout(const MsmPlan& pl, size_t x_bytes, size_t aff_bytes) {  // sizes of one XYZZ / affine image
     MsmWorkspace ws;
     size_t o = 0;
     const size_t nk = pl.nkeys;
@@ -293,18 +309,19 @@ inline MsmWorkspace msm_layout(const MsmPlan& pl) {
     ws.toff = o, o = msm_align(o + 4 * (nk + 1));
     ws.part = o, o = msm_align(o + 4 * (nch + 1));
     ws.entries = o, o = msm_align(o + 4 * ((size_t)pl.n * pl.W + 1));
-    ws.partial = o, o = msm_align(o + sizeof(G1XRaw) * pl.max_tasks);
-    ws.bucket = o, o = msm_align(o + sizeof(G1XRaw) * nk);
-    ws.chunk_out = o, o = msm_align(o + sizeof(G1XRaw) * (size_t)pl.W * pl.nchunks);
-    ws.win = o, o = msm_align(o + sizeof(G1XRaw) * pl.W);
-    ws.out = o, o = msm_align(o + 16 * 8);
+    ws.partial = o, o = msm_align(o + x_bytes * pl.max_tasks);
+    ws.bucket = o, o = msm_align(o + x_bytes * nk);
+    ws.chunk_out = o, o = msm_align(o + x_bytes * (size_t)pl.W * pl.nchunks);
+    ws.win = o, o = msm_align(o + x_bytes * pl.W);
+    ws.out = o, o = msm_align(o + 2 * aff_bytes);
     ws.bytes = o;
     return ws;
 }
 
-// Enqueues one multi-exponentiation on the executor.  `base` is a device buffer of at least msm_layout(pl).bytes; the result
-// (16 words, see msm_store_result) lands at base + ws.out, the error flag at base + ws.err.  Returns the number of launches.
-template <class Exec>
+// Enqueues one multi-exponentiation on curve C (G1 or G2) on the executor.  `base` is a device buffer of at least
+// msm_layout(pl, 8 * C::X_WORDS, 8 * C::AFF_WORDS).bytes; the result (2 * AFF_WORDS words, see msm_store_result) lands at
+// base + ws.out, the error flag at base + ws.err.  Returns the number of launches.
+template <class C, class Exec>
 int msm_enqueue(Exec& ex, const MsmPlan& pl, const MsmWorkspace& ws, unsigned char* base, const uint64_t* d_points, const uint64_t* d_scalars) {
     uint32_t* count = (uint32_t*)(base + ws.count);
     uint32_t* cursor = (uint32_t*)(base + ws.cursor);
@@ -314,10 +331,10 @@ int msm_enqueue(Exec& ex, const MsmPlan& pl, const MsmWorkspace& ws, unsigned ch
     uint32_t* toff = (uint32_t*)(base + ws.toff);
     uint32_t* part = (uint32_t*)(base + ws.part);
     uint32_t* entries = (uint32_t*)(base + ws.entries);
-    G1XRaw* partial = (G1XRaw*)(base + ws.partial);
-    G1XRaw* bucket = (G1XRaw*)(base + ws.bucket);
-    G1XRaw* chunk_out = (G1XRaw*)(base + ws.chunk_out);
-    G1XRaw* win = (G1XRaw*)(base + ws.win);
+    uint64_t* partial = (uint64_t*)(base + ws.partial);
+    uint64_t* bucket = (uint64_t*)(base + ws.bucket);
+    uint64_t* chunk_out = (uint64_t*)(base + ws.chunk_out);
+    uint64_t* win = (uint64_t*)(base + ws.win);
     uint64_t* out = (uint64_t*)(base + ws.out);
     const uint32_t nk = pl.nkeys, sl = pl.scan_L, nch = (nk + sl - 1) / sl;
     int launches = 0;
@@ -331,12 +348,12 @@ int msm_enqueue(Exec& ex, const MsmPlan& pl, const MsmWorkspace& ws, unsigned ch
     launches += ex.template launch<KScanA>(nch, (const uint32_t*)tcount, part, nk, sl);
     launches += ex.template launch<KScanB>(1, part, nch);
     launches += ex.template launch<KScanC>(nch, (const uint32_t*)tcount, toff, (const uint32_t*)part, nk, sl, nch);
-    launches += ex.template launch<KAccum>(pl.max_tasks, pl, d_points, (const uint32_t*)entries, (const uint32_t*)off, (const uint32_t*)count,
-                                           (const uint32_t*)toff, partial);
-    launches += ex.template launch<KBucket>(nk, (const uint32_t*)toff, (const G1XRaw*)partial, bucket);
-    launches += ex.template launch<KChunk>((size_t)pl.W * pl.nchunks, pl, (const G1XRaw*)bucket, chunk_out);
-    launches += ex.template launch<KWindow>(pl.W, pl, (const G1XRaw*)chunk_out, win);
-    launches += ex.template launch<KFinal>(1, pl, (const G1XRaw*)win, out);
+    launches += ex.template launch<KAccum<C>>(pl.max_tasks, pl, d_points, (const uint32_t*)entries, (const uint32_t*)off, (const uint32_t*)count,
+                                              (const uint32_t*)toff, partial);
+    launches += ex.template launch<KBucket<C>>(nk, (const uint32_t*)toff, (const uint64_t*)partial, bucket);
+    launches += ex.template launch<KChunk<C>>((size_t)pl.W * pl.nchunks, pl, (const uint64_t*)bucket, chunk_out);
+    launches += ex.template launch<KWindow<C>>(pl.W, pl, (const uint64_t*)chunk_out, win);
+    launches += ex.template launch<KFinal<C>>(1, pl, (const uint64_t*)win, out);
     return launches;
 }
 

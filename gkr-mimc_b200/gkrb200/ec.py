@@ -5,6 +5,7 @@
     pk.pubKGkr / pk.privKGkrSigma []bn254.G1Affine (setup.go:32,116-121)   EcContext.SetBases(slot, points)
     G1Affine.MultiExp(points, scalars, ecc.MultiExpConfig{})               EcContext.MultiExp(slot, scalars) / MultiExpPoints
     G1Affine.Add (hints.go:184)                                            EcContext.Add(a, b)
+    G2Affine.MultiExp(pk.G2.B, wireValuesB, cfg) (prove.go:277)            EcContext.SetBasesG2 / MultiExpG2 / MultiExpPointsG2 / AddG2
     DeriveRandomnessFromPoint(g1) (hints.go:147-159)                       DeriveRandomnessFromPoint(g1)
     InitialRandomnessHint.Call (hints.go:162-192)                          EcContext.InitialRandomnessHint(...)
     fft.NewDomain(m, 1, true) (groth16/setup.go:98)                        EcContext.NewDomain(m)
@@ -75,6 +76,11 @@ def lib():
     L.gkrb200ec_g1_multiexp_points.argtypes = [vp, vp, vp, sz, i32, vp]
     L.gkrb200ec_initial_randomness.argtypes = [vp, i32, vp, sz, i32, vp, sz, i32, vp, vp]
     L.gkrb200ec_g1_add.argtypes = [vp, vp, vp, vp]
+    L.gkrb200ec_g2_set_bases.argtypes = [vp, i32, vp, sz]
+    L.gkrb200ec_g2_multiexp.argtypes = [vp, i32, vp, sz, i32, vp]
+    L.gkrb200ec_g2_multiexp_device.argtypes = [vp, i32, vp, sz, i32, vp]
+    L.gkrb200ec_g2_multiexp_points.argtypes = [vp, vp, vp, sz, i32, vp]
+    L.gkrb200ec_g2_add.argtypes = [vp, vp, vp, vp]
     L.gkrb200ec_g1_raw_bytes.argtypes = [vp, vp]
     L.gkrb200ec_keccak256.argtypes = [vp, sz, vp]
     L.gkrb200ec_derive_randomness_from_point.argtypes = [vp, vp]
@@ -103,6 +109,13 @@ def g1_array(a):
     a = np.ascontiguousarray(a, dtype=np.uint64)
     if a.shape[-1] != 8:
         raise ValueError("G1Affine points must have a trailing dimension of 8 uint64 limbs")
+    return a
+
+
+def g2_array(a):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if a.shape[-1] != 16:
+        raise ValueError("G2Affine points must have a trailing dimension of 16 uint64 limbs (X.A0, X.A1, Y.A0, Y.A1)")
     return a
 
 
@@ -204,6 +217,38 @@ class EcContext:
         check(lib().gkrb200ec_initial_randomness(self._h, slot_pub, _p(sp) if sp.shape[0] else None, sp.shape[0], slot_priv,
                                                  _p(sq) if sq.shape[0] else None, sq.shape[0], form, _p(krs_priv), _p(rnd)))
         return krs_priv, rnd
+
+    # ---- G2 (prove.go:277: Bs.MultiExp(pk.G2.B, wireValuesB, ...))
+    def SetBasesG2(self, slot, points):
+        points = g2_array(points).reshape(-1, 16)
+        check(lib().gkrb200ec_g2_set_bases(self._h, slot, _p(points) if points.shape[0] else None, points.shape[0]))
+
+    def MultiExpG2(self, slot, scalars, form=SCALARS_REGULAR):
+        """res.MultiExp(basesG2[slot][:len(scalars)], scalars, ecc.MultiExpConfig{}) -> (16,) G2Affine"""
+        scalars = fr_array(scalars).reshape(-1, 4)
+        out = np.zeros(16, dtype=np.uint64)
+        check(lib().gkrb200ec_g2_multiexp(self._h, slot, _p(scalars) if scalars.shape[0] else None, scalars.shape[0], form, _p(out)))
+        return out
+
+    def MultiExpG2Device(self, slot, d_scalars_ptr, n, form=SCALARS_REGULAR):
+        out = np.zeros(16, dtype=np.uint64)
+        check(lib().gkrb200ec_g2_multiexp_device(self._h, slot, ctypes.c_void_p(d_scalars_ptr), n, form, _p(out)))
+        return out
+
+    def MultiExpPointsG2(self, points, scalars, form=SCALARS_REGULAR):
+        points, scalars = g2_array(points).reshape(-1, 16), fr_array(scalars).reshape(-1, 4)
+        if points.shape[0] != scalars.shape[0]:
+            raise ValueError("len(points) != len(scalars)")
+        out = np.zeros(16, dtype=np.uint64)
+        n = points.shape[0]
+        check(lib().gkrb200ec_g2_multiexp_points(self._h, _p(points) if n else None, _p(scalars) if n else None, n, form, _p(out)))
+        return out
+
+    def AddG2(self, a, b):
+        a, b = g2_array(a).reshape(16), g2_array(b).reshape(16)
+        out = np.zeros(16, dtype=np.uint64)
+        check(lib().gkrb200ec_g2_add(self._h, _p(a), _p(b), _p(out)))
+        return out
 
     # ---- fft.Domain / computeH
     def NewDomain(self, m):

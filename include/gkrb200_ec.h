@@ -5,10 +5,10 @@
  *   prover/gadget/hints.go:182-183   InitialRandomnessHint: the 3N GKR inputs/outputs against pubKGkr / privKGkrSigma
  *   prover/gadget/prove.go:76,91     KrsNotGkr / KrsPrivNotGkr
  *   prover/gadget/prove.go:189,202,221   Bs1, Ar, Krs2 (the G1 multi-exponentiations of ComputeGroth16Proof)
+ *   prover/gadget/prove.go:277       Bs: the G2 multi-exponentiation
  *   prover/gadget/prove.go:310-366   computeH: seven FFTs over the constraint domain
  * This library is those operations on the device, plus the rest of InitialRandomnessHint.Call (hints.go:147-192).  Each entry
- * point names the Go interface it replaces; the cgo binding is in INTEGRATION.md section 7.  The G2 multi-exponentiation
- * (prove.go:277) is not here.
+ * point names the Go interface it replaces; the cgo binding is in INTEGRATION.md section 7.
  *
  * Data at the boundary is Go memory, unchanged:
  *   []bn254.G1Affine  = 8 x uint64 per point: X then Y, fp.Element = 4 little-endian limbs, Montgomery form (v * 2^256 mod p),
@@ -74,6 +74,17 @@ int gkrb200ec_initial_randomness(gkrb200ec_ctx *ctx, int slot_pub, const uint64_
 
 /* G1Affine.Add on the device (hints.go:184); a, b, out: 8 words each                                                          */
 int gkrb200ec_g1_add(gkrb200ec_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out);
+
+/* ---- G2: Bs.MultiExp(pk.G2.B, wireValuesB, ...) (prover/gadget/prove.go:277) -------------------------------------------------
+ * []bn254.G2Affine = 16 x uint64 per point: X.A0, X.A1, Y.A0, Y.A1 (fptower.E2 = {A0, A1 fp.Element}, value A0 + A1 u, u^2 = -1),
+ * Montgomery form, infinity all zero.  Same kernels as G1 over the quadratic extension; slots are shared with G1 (a slot holds
+ * one kind of point, and using it with the other kind's entry points is GKRB200EC_ERR_ARG).                                     */
+int gkrb200ec_g2_set_bases(gkrb200ec_ctx *ctx, int slot, const uint64_t *points, size_t n);
+int gkrb200ec_g2_multiexp(gkrb200ec_ctx *ctx, int slot, const uint64_t *scalars, size_t n, int scalar_form, uint64_t *out);
+int gkrb200ec_g2_multiexp_device(gkrb200ec_ctx *ctx, int slot, const void *d_scalars, size_t n, int scalar_form, uint64_t *out);
+int gkrb200ec_g2_multiexp_points(gkrb200ec_ctx *ctx, const uint64_t *points, const uint64_t *scalars, size_t n, int scalar_form,
+                                 uint64_t *out);
+int gkrb200ec_g2_add(gkrb200ec_ctx *ctx, const uint64_t *a, const uint64_t *b, uint64_t *out);
 
 /* Host-side pieces of DeriveRandomnessFromPoint (hints.go:147-159); no device involved.
  * gkrb200ec_g1_raw_bytes: G1Affine.RawBytes (X || Y big-endian, regular form; 0x40 then zeros for infinity)

@@ -167,3 +167,63 @@ def initial_randomness(pub_points, pub_scalars, priv_points, priv_scalars, mont=
     lib().orc_initial_randomness(_p(pp), _p(ps), ctypes.c_size_t(pp.shape[0]), _p(qp), _p(qs), ctypes.c_size_t(qp.shape[0]),
                                  ctypes.c_int(1 if mont else 0), ctypes.c_int(threads()), _p(krs_priv), _p(rnd))
     return krs_priv, rnd
+
+
+# ------------------------------------------------------------ G2 (points: (..., 16) uint64 = []bn254.G2Affine: X.A0, X.A1, Y.A0, Y.A1)
+def g2_generator():
+    out = np.zeros(16, dtype=np.uint64)
+    lib().orc_g2_generator(_p(out))
+    return out
+
+
+def g2_is_on_curve(pt):
+    pt = _c(pt, 16)
+    lib().orc_g2_is_on_curve.restype = ctypes.c_int
+    return bool(lib().orc_g2_is_on_curve(_p(pt)))
+
+
+def g2_add(a, b):
+    a, b = _c(a, 16), _c(b, 16)
+    out = np.zeros(16, dtype=np.uint64)
+    lib().orc_g2_add(_p(a), _p(b), _p(out))
+    return out
+
+
+def g2_neg(a):
+    a = _c(a, 16)
+    out = np.zeros(16, dtype=np.uint64)
+    lib().orc_g2_neg(_p(a), _p(out))
+    return out
+
+
+def g2_scalar_mul(pt, k):
+    pt = _c(pt, 16)
+    kk = np.array(limbs(k % Q), dtype=np.uint64)
+    out = np.zeros(16, dtype=np.uint64)
+    lib().orc_g2_scalar_mul(_p(pt), _p(kk), _p(out))
+    return out
+
+
+def g2_multiexp(points, scalars, mont=False, nthreads=None):
+    points, scalars = _c(points, 16).reshape(-1, 16), _c(scalars, 4).reshape(-1, 4)
+    assert points.shape[0] == scalars.shape[0]
+    out = np.zeros(16, dtype=np.uint64)
+    lib().orc_g2_multiexp(_p(points), _p(scalars), ctypes.c_size_t(points.shape[0]), ctypes.c_int(1 if mont else 0),
+                          ctypes.c_int(nthreads or threads()), _p(out))
+    return out
+
+
+def g2_gen_points(n, a=0x7654321, b=0xD1B54A32D192ED03):
+    """P_i = (a + i*b) * G2gen, i < n"""
+    out = np.zeros((n, 16), dtype=np.uint64)
+    aa, bb = np.array(limbs(a % Q), dtype=np.uint64), np.array(limbs(b % Q), dtype=np.uint64)
+    if n:
+        lib().orc_g2_gen_points(ctypes.c_size_t(n), _p(aa), _p(bb), _p(out))
+    return out
+
+
+def g2_point_to_ints(pt):
+    """(16,) Montgomery limbs -> ((x0, x1), (y0, y1)) python ints"""
+    pt = np.asarray(pt, dtype=np.uint64).reshape(16)
+    v = [unlimbs(pt[4 * k:4 * k + 4]) * RP_INV % P for k in range(4)]
+    return ((v[0], v[1]), (v[2], v[3]))

@@ -492,3 +492,283 @@ void orc_initial_randomness(const uint64_t *pub_points, const uint64_t *pub_scal
     orc_g1_add(krs, krs_gkr_priv, krs);
     orc_derive_randomness_from_point(krs, randomness);
 }
+
+/* =================================================================================================================================
+ * G2: y^2 = x^3 + 3/(9+u) over Fp2 = Fp[u]/(u^2+1) -- G2Affine.MultiExp (prover/gadget/prove.go:277, Bs).
+ * gnark-crypto bn254.G2Affine = {X, Y fptower.E2}, E2 = {A0, A1 fp.Element}: 16 words, Montgomery, infinity all zero.
+ * Fp2 products are SCHOOLBOOK here (four base products; the product library uses Karatsuba and complex squaring) and the group law
+ * is Jacobian (the product uses XYZZ), one double-and-add per point, summed.
+ * Pinning: the published generator of G2 (EIP-197 / gnark-crypto) must satisfy the curve equation and have order q
+ * (tests/test_msm_cpu.py), and agreement with the Python big-integer restatement in oracle/pyref_msm.py.
+ * ================================================================================================================================= */
+typedef struct { fp_t a0, a1; } f2_t;
+typedef struct { f2_t x, y; } aff2_t;
+typedef struct { f2_t x, y, z; } jac2_t;
+
+static void f2_add(f2_t *z, const f2_t *x, const f2_t *y) { fp_add(&z->a0, &x->a0, &y->a0); fp_add(&z->a1, &x->a1, &y->a1); }
+static void f2_sub(f2_t *z, const f2_t *x, const f2_t *y) { fp_sub(&z->a0, &x->a0, &y->a0); fp_sub(&z->a1, &x->a1, &y->a1); }
+static void f2_mul(f2_t *z, const f2_t *x, const f2_t *y) {
+    fp_t t0, t1, t2, t3;
+    fp_mul(&t0, &x->a0, &y->a0);
+    fp_mul(&t1, &x->a1, &y->a1);
+    fp_mul(&t2, &x->a0, &y->a1);
+    fp_mul(&t3, &x->a1, &y->a0);
+    fp_sub(&z->a0, &t0, &t1);
+    fp_add(&z->a1, &t2, &t3);
+}
+static void f2_sqr(f2_t *z, const f2_t *x) { f2_t t = *x; f2_mul(z, &t, &t); }
+static int f2_is_zero(const f2_t *x) { return fp_is_zero(&x->a0) && fp_is_zero(&x->a1); }
+static int f2_eq(const f2_t *x, const f2_t *y) { return fp_eq(&x->a0, &y->a0) && fp_eq(&x->a1, &y->a1); }
+static void f2_inv(f2_t *z, const f2_t *x) { /* conj(x) / (a0^2 + a1^2) */
+    fp_t n, t, ni, zero = {{0, 0, 0, 0}};
+    fp_sqr(&n, &x->a0);
+    fp_sqr(&t, &x->a1);
+    fp_add(&n, &n, &t);
+    fp_inv(&ni, &n);
+    fp_mul(&z->a0, &x->a0, &ni);
+    fp_mul(&t, &x->a1, &ni);
+    fp_sub(&z->a1, &zero, &t);
+}
+static void f2_set_one(f2_t *z) { memcpy(z->a0.l, FP_ONE, 32); memset(z->a1.l, 0, 32); }
+
+static int aff2_is_inf(const aff2_t *p) { return f2_is_zero(&p->x) && f2_is_zero(&p->y); }
+static void jac2_set_inf(jac2_t *p) { memset(p, 0, sizeof *p); }
+static void jac2_from_aff(jac2_t *r, const aff2_t *p) {
+    if (aff2_is_inf(p)) { jac2_set_inf(r); return; }
+    r->x = p->x;
+    r->y = p->y;
+    f2_set_one(&r->z);
+}
+static void jac2_dbl(jac2_t *r, const jac2_t *p) { /* dbl-2009-l, a = 0 */
+    if (f2_is_zero(&p->z)) { jac2_set_inf(r); return; }
+    f2_t a, b, c, d, e, f, t, x3, y3, z3;
+    f2_sqr(&a, &p->x);
+    f2_sqr(&b, &p->y);
+    f2_sqr(&c, &b);
+    f2_add(&t, &p->x, &b);
+    f2_sqr(&t, &t);
+    f2_sub(&t, &t, &a);
+    f2_sub(&t, &t, &c);
+    f2_add(&d, &t, &t);
+    f2_add(&e, &a, &a);
+    f2_add(&e, &e, &a);
+    f2_sqr(&f, &e);
+    f2_sub(&x3, &f, &d);
+    f2_sub(&x3, &x3, &d);
+    f2_sub(&t, &d, &x3);
+    f2_mul(&y3, &e, &t);
+    f2_add(&c, &c, &c);
+    f2_add(&c, &c, &c);
+    f2_add(&c, &c, &c);
+    f2_sub(&y3, &y3, &c);
+    f2_mul(&z3, &p->y, &p->z);
+    f2_add(&z3, &z3, &z3);
+    r->x = x3; r->y = y3; r->z = z3;
+}
+static void jac2_add(jac2_t *r, const jac2_t *p, const jac2_t *q) { /* add-2007-bl with the special cases */
+    if (f2_is_zero(&p->z)) { *r = *q; return; }
+    if (f2_is_zero(&q->z)) { *r = *p; return; }
+    f2_t z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v, t, x3, y3, z3;
+    f2_sqr(&z1z1, &p->z);
+    f2_sqr(&z2z2, &q->z);
+    f2_mul(&u1, &p->x, &z2z2);
+    f2_mul(&u2, &q->x, &z1z1);
+    f2_mul(&s1, &p->y, &q->z);
+    f2_mul(&s1, &s1, &z2z2);
+    f2_mul(&s2, &q->y, &p->z);
+    f2_mul(&s2, &s2, &z1z1);
+    if (f2_eq(&u1, &u2)) {
+        if (f2_eq(&s1, &s2)) jac2_dbl(r, p);
+        else jac2_set_inf(r);
+        return;
+    }
+    f2_sub(&h, &u2, &u1);
+    f2_add(&i, &h, &h);
+    f2_sqr(&i, &i);
+    f2_mul(&j, &h, &i);
+    f2_sub(&rr, &s2, &s1);
+    f2_add(&rr, &rr, &rr);
+    f2_mul(&v, &u1, &i);
+    f2_sqr(&x3, &rr);
+    f2_sub(&x3, &x3, &j);
+    f2_sub(&x3, &x3, &v);
+    f2_sub(&x3, &x3, &v);
+    f2_sub(&t, &v, &x3);
+    f2_mul(&y3, &rr, &t);
+    f2_mul(&t, &s1, &j);
+    f2_add(&t, &t, &t);
+    f2_sub(&y3, &y3, &t);
+    f2_add(&z3, &p->z, &q->z);
+    f2_sqr(&z3, &z3);
+    f2_sub(&z3, &z3, &z1z1);
+    f2_sub(&z3, &z3, &z2z2);
+    f2_mul(&z3, &z3, &h);
+    r->x = x3; r->y = y3; r->z = z3;
+}
+static void jac2_to_aff(aff2_t *r, const jac2_t *p) {
+    if (f2_is_zero(&p->z)) { memset(r, 0, sizeof *r); return; }
+    f2_t zi, zi2, zi3;
+    f2_inv(&zi, &p->z);
+    f2_sqr(&zi2, &zi);
+    f2_mul(&zi3, &zi2, &zi);
+    f2_mul(&r->x, &p->x, &zi2);
+    f2_mul(&r->y, &p->y, &zi3);
+}
+static void jac2_scalar_mul(jac2_t *r, const aff2_t *p, const uint64_t k[4]) {
+    jac2_t acc, base;
+    jac2_set_inf(&acc);
+    jac2_from_aff(&base, p);
+    for (int i = 255; i >= 0; i--) {
+        jac2_dbl(&acc, &acc);
+        if ((k[i / 64] >> (i % 64)) & 1) jac2_add(&acc, &acc, &base);
+    }
+    *r = acc;
+}
+
+/* the generator of G2 (EIP-197 / gnark-crypto bn254.Generators), regular form, little-endian limbs: X.A0, X.A1, Y.A0, Y.A1 */
+static const uint64_t G2_GEN[16] = {
+    0x46debd5cd992f6edULL, 0x674322d4f75edaddULL, 0x426a00665e5c4479ULL, 0x1800deef121f1e76ULL, /* 10857046999023057135944570762232829481370756359578518086990519993285655852781 */
+    0x97e485b7aef312c2ULL, 0xf1aa493335a9e712ULL, 0x7260bfb731fb5d25ULL, 0x198e9393920d483aULL, /* 11559732032986387107991004021392285783925812861821192530917403151452391805634 */
+    0x4ce6cc0166fa7daaULL, 0xe3d1e7690c43d37bULL, 0x4aab71808dcb408fULL, 0x12c85ea5db8c6debULL, /* 8495653923123431417604973247489272438418190587263600148770280649306958101930 */
+    0x55acdadcd122975bULL, 0xbc4b313370b38ef3ULL, 0xec9e99ad690c3395ULL, 0x090689d0585ff075ULL, /* 4082367875863433681332203403145435568316851327593401208105741076214120093531 */
+};
+void orc_g2_generator(uint64_t *out) {
+    for (int k = 0; k < 4; k++) orc_fp_to_mont(G2_GEN + 4 * k, out + 4 * k);
+}
+int orc_g2_is_on_curve(const uint64_t *pt) { /* y^2 = x^3 + 3/(9+u) */
+    aff2_t p;
+    memcpy(&p, pt, 128);
+    if (aff2_is_inf(&p)) return 1;
+    f2_t nine_u, three, b, y2, x3;
+    fp_t nine = {{9, 0, 0, 0}}, one = {{1, 0, 0, 0}}, thr = {{3, 0, 0, 0}};
+    fp_to_mont(&nine_u.a0, &nine);
+    fp_to_mont(&nine_u.a1, &one);
+    fp_to_mont(&three.a0, &thr);
+    memset(three.a1.l, 0, 32);
+    f2_inv(&b, &nine_u);
+    f2_mul(&b, &b, &three);
+    f2_sqr(&y2, &p.y);
+    f2_sqr(&x3, &p.x);
+    f2_mul(&x3, &x3, &p.x);
+    f2_add(&x3, &x3, &b);
+    return f2_eq(&y2, &x3);
+}
+void orc_g2_add(const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    aff2_t pa, pb, r;
+    jac2_t ja, jb, js;
+    memcpy(&pa, a, 128);
+    memcpy(&pb, b, 128);
+    jac2_from_aff(&ja, &pa);
+    jac2_from_aff(&jb, &pb);
+    jac2_add(&js, &ja, &jb);
+    jac2_to_aff(&r, &js);
+    memcpy(out, &r, 128);
+}
+void orc_g2_neg(const uint64_t *a, uint64_t *out) {
+    aff2_t p;
+    f2_t zero;
+    memcpy(&p, a, 128);
+    memset(&zero, 0, sizeof zero);
+    if (!aff2_is_inf(&p)) f2_sub(&p.y, &zero, &p.y);
+    memcpy(out, &p, 128);
+}
+void orc_g2_scalar_mul(const uint64_t *pt, const uint64_t *k_regular, uint64_t *out) {
+    aff2_t p, r;
+    jac2_t j;
+    memcpy(&p, pt, 128);
+    jac2_scalar_mul(&j, &p, k_regular);
+    jac2_to_aff(&r, &j);
+    memcpy(out, &r, 128);
+}
+typedef struct {
+    const uint64_t *points, *scalars;
+    size_t lo, hi;
+    int scalars_mont;
+    jac2_t sum;
+} msm2_job;
+static void *msm2_worker(void *arg) {
+    msm2_job *j = (msm2_job *)arg;
+    jac2_set_inf(&j->sum);
+    for (size_t i = j->lo; i < j->hi; i++) {
+        aff2_t p;
+        uint64_t k[4];
+        memcpy(&p, j->points + 16 * i, 128);
+        if (j->scalars_mont) orc_fr_from_mont(j->scalars + 4 * i, k);
+        else memcpy(k, j->scalars + 4 * i, 32);
+        jac2_t t;
+        jac2_scalar_mul(&t, &p, k);
+        jac2_add(&j->sum, &j->sum, &t);
+    }
+    return NULL;
+}
+/* G2Affine.MultiExp(points, scalars) */
+void orc_g2_multiexp(const uint64_t *points, const uint64_t *scalars, size_t n, int scalars_mont, int threads, uint64_t *out) {
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = n ? (int)n : 1;
+    msm2_job *jobs = (msm2_job *)calloc((size_t)threads, sizeof(msm2_job));
+    pthread_t *th = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; t++) {
+        jobs[t].points = points;
+        jobs[t].scalars = scalars;
+        jobs[t].scalars_mont = scalars_mont;
+        jobs[t].lo = n * (size_t)t / (size_t)threads;
+        jobs[t].hi = n * (size_t)(t + 1) / (size_t)threads;
+        pthread_create(&th[t], NULL, msm2_worker, &jobs[t]);
+    }
+    jac2_t acc;
+    jac2_set_inf(&acc);
+    for (int t = 0; t < threads; t++) {
+        pthread_join(th[t], NULL);
+        jac2_add(&acc, &acc, &jobs[t].sum);
+    }
+    aff2_t r;
+    jac2_to_aff(&r, &acc);
+    memcpy(out, &r, 128);
+    free(jobs);
+    free(th);
+}
+/* P_i = (a + i*b) * G2gen, i < n: bases with a known discrete log (closed-form check of a multi-exponentiation at any size) */
+void orc_g2_gen_points(size_t n, const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    uint64_t g[16];
+    orc_g2_generator(g);
+    aff2_t ga;
+    memcpy(&ga, g, 128);
+    jac2_t cur, step;
+    jac2_scalar_mul(&cur, &ga, a);
+    jac2_scalar_mul(&step, &ga, b);
+    enum { BLK2 = 256 };
+    jac2_t *blk = (jac2_t *)malloc(sizeof(jac2_t) * BLK2);
+    f2_t *pref = (f2_t *)malloc(sizeof(f2_t) * BLK2);
+    for (size_t base = 0; base < n; base += BLK2) {
+        size_t m = n - base < BLK2 ? n - base : BLK2;
+        for (size_t i = 0; i < m; i++) {
+            blk[i] = cur;
+            jac2_add(&cur, &cur, &step);
+        }
+        f2_t acc;
+        f2_set_one(&acc);
+        for (size_t i = 0; i < m; i++) {
+            pref[i] = acc;
+            if (!f2_is_zero(&blk[i].z)) f2_mul(&acc, &acc, &blk[i].z);
+        }
+        f2_t inv;
+        f2_inv(&inv, &acc);
+        for (size_t i = m; i-- > 0;) {
+            aff2_t r;
+            if (f2_is_zero(&blk[i].z)) {
+                memset(&r, 0, sizeof r);
+            } else {
+                f2_t zi, zi2, zi3;
+                f2_mul(&zi, &inv, &pref[i]);
+                f2_mul(&inv, &inv, &blk[i].z);
+                f2_sqr(&zi2, &zi);
+                f2_mul(&zi3, &zi2, &zi);
+                f2_mul(&r.x, &blk[i].x, &zi2);
+                f2_mul(&r.y, &blk[i].y, &zi3);
+            }
+            memcpy(out + 16 * (base + i), &r, 128);
+        }
+    }
+    free(blk);
+    free(pref);
+}

@@ -123,3 +123,71 @@ def initial_randomness(pub_points, pub_scalars, priv_points, priv_scalars):
     krs = multi_exp(pub_points, pub_scalars)
     krs_priv = multi_exp(priv_points, priv_scalars)
     return krs_priv, derive_randomness_from_point(add(krs, krs_priv))
+
+
+# ---- G2: y^2 = x^3 + 3/(9+u) over Fp2 = Fp[u]/(u^2+1); G2Affine.MultiExp (prover/gadget/prove.go:277).  Elements are pairs (a0, a1).
+def f2_mul(a, b):
+    return ((a[0] * b[0] - a[1] * b[1]) % P, (a[0] * b[1] + a[1] * b[0]) % P)
+
+
+def f2_inv(a):
+    n = pow(a[0] * a[0] + a[1] * a[1], -1, P)
+    return (a[0] * n % P, (-a[1] * n) % P)
+
+
+def f2_add(a, b):
+    return ((a[0] + b[0]) % P, (a[1] + b[1]) % P)
+
+
+def f2_sub(a, b):
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+B2 = f2_mul((3, 0), f2_inv((9, 1)))
+G2 = ((10857046999023057135944570762232829481370756359578518086990519993285655852781,
+       11559732032986387107991004021392285783925812861821192530917403151452391805634),
+      (8495653923123431417604973247489272438418190587263600148770280649306958101930,
+       4082367875863433681332203403145435568316851327593401208105741076214120093531))  # EIP-197 / gnark-crypto bn254.Generators
+INF2 = ((0, 0), (0, 0))
+
+
+def g2_is_on_curve(pt):
+    x, y = pt
+    return pt == INF2 or f2_mul(y, y) == f2_add(f2_mul(f2_mul(x, x), x), B2)
+
+
+def g2_add(p1, p2):
+    if p1 == INF2:
+        return p2
+    if p2 == INF2:
+        return p1
+    (x1, y1), (x2, y2) = p1, p2
+    if x1 == x2:
+        if f2_add(y1, y2) == (0, 0):
+            return INF2
+        lam = f2_mul(f2_mul((3, 0), f2_mul(x1, x1)), f2_inv(f2_add(y1, y1)))
+    else:
+        lam = f2_mul(f2_sub(y2, y1), f2_inv(f2_sub(x2, x1)))
+    x3 = f2_sub(f2_sub(f2_mul(lam, lam), x1), x2)
+    return (x3, f2_sub(f2_mul(lam, f2_sub(x1, x3)), y1))
+
+
+def g2_neg(pt):
+    return pt if pt == INF2 else (pt[0], ((-pt[1][0]) % P, (-pt[1][1]) % P))
+
+
+def g2_mul(k, pt):
+    acc, base = INF2, pt
+    while k:
+        if k & 1:
+            acc = g2_add(acc, base)
+        base = g2_add(base, base)
+        k >>= 1
+    return acc
+
+
+def g2_multi_exp(points, scalars):
+    acc = INF2
+    for pt, s in zip(points, scalars):
+        acc = g2_add(acc, g2_mul(s % Q, pt))
+    return acc

@@ -1,6 +1,6 @@
 // CPU emulation of the multi-exponentiation and FFT kernels -- TEST INFRASTRUCTURE, never shipped or loaded by the product.
 //
-// Compiles the product headers gkr-mimc_b200/csrc/ec/{field,g1,msm,ntt}.cuh with a plain C++ compiler: every kernel body is a function of
+// Compiles the product headers gkr-mimc_b200/csrc/ec/{field,curve,msm,ntt}.cuh with a plain C++ compiler: every kernel body is a function of
 // its thread index, and the executor below runs each "launch" as a loop.  Host-side, field.cuh's carry-chain primitives are plain
 // 64-bit C++ with the semantics of the inline-PTX ones the device uses (those are exercised on the GPU by every GKR parity test).
 // tests/test_msm_cpu.py and tests/test_ntt_cpu.py drive this against the oracles, so the digit decomposition, counting sort, task
@@ -72,68 +72,97 @@ void emu_field_op(int field, int op, const uint64_t* a, const uint64_t* b, size_
     }
 }
 
-// XYZZ operations on affine inputs, result affine (Montgomery).  op: 0 madd (a as XYZZ + affine b), 1 full add, 2 double a,
-// 3 k * a with k = b[0] (small), 4 madd after re-randomising a's representation (a = 3a - 2a path: a non-trivial ZZ)
-void emu_g1_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
-    const G1Affine pa = g1_aff_load(a);
-    G1X r = g1x_inf();
-    if (op == 0) r = g1x_add_affine<MulInline>(g1x_from_affine(pa), g1_aff_load(b));
-    else if (op == 1) r = g1x_add<MulCall>(g1x_from_affine(pa), g1x_from_affine(g1_aff_load(b)));
-    else if (op == 2) r = g1x_dbl<MulCall>(g1x_from_affine(pa));
-    else if (op == 3) r = g1x_mul_small<MulCall>(g1x_from_affine(pa), (uint32_t)b[0]);
-    else if (op == 4) {
-        // a written as (2a + 2a) - 3a ... : build a with ZZ != 1 through doublings and additions, then add b
-        G1X t = g1x_dbl<MulInline>(g1x_from_affine(pa));       // 2a
-        t = g1x_add_affine<MulInline>(t, pa);                   // 3a
-        G1Affine na = pa;
-        na.y = f_neg<Fp>(na.y);
-        t = g1x_add_affine<MulInline>(t, na);                   // 2a
-        t = g1x_add_affine<MulInline>(t, na);                   // a, ZZ != 1
-        r = g1x_add_affine<MulInline>(t, g1_aff_load(b));       // a + b incl. the doubling / cancellation cases on a non-trivial ZZ
-    } else if (op == 5) {
-        G1X t = g1x_dbl<MulCall>(g1x_from_affine(pa));
-        G1Affine na = pa;
-        na.y = f_neg<Fp>(na.y);
-        t = g1x_add_affine<MulCall>(t, na);  // a, ZZ != 1
-        G1X u = g1x_dbl<MulCall>(g1x_from_affine(g1_aff_load(b)));
-        G1Affine nb = g1_aff_load(b);
-        nb.y = f_neg<Fp>(nb.y);
-        u = g1x_add_affine<MulCall>(u, nb);  // b, ZZ != 1
-        r = g1x_add<MulCall>(t, u);
-    }
-    g1_aff_store(out, g1x_to_affine(r));
-}
+}  // extern "C"
 
-// The whole multi-exponentiation through msm_enqueue on the host executor.  out16 as the device writes it; returns the error flag,
-// or -1 when the plan does not fit.  reverse != 0 runs every launch's threads in descending order.
-int emu_msm(const uint64_t* points, const uint64_t* scalars, size_t n, int scalars_mont, int c_force, int t_force, int reverse, uint64_t* out16,
-            uint32_t* plan_out) {
+namespace {
+// XYZZ operations on affine inputs, result affine (Montgomery), on curve C.  op: 0 madd (a as XYZZ + affine b), 1 full add,
+// 2 double a, 3 k * a with k = b[0] (small), 4 madd onto a non-trivial representation of a (ZZ != 1), incl. the doubling /
+// cancellation cases, 5 full add of two non-trivial representations
+template <class C>
+void g_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) {
+    typedef typename C::MInline MI;
+    typedef typename C::MCall MC;
+    const typename C::Affine pa = C::aff_load(a);
+    typename C::X r = C::x_inf();
+    if (op == 0) r = C::template add_affine<MI>(C::from_affine(pa), C::aff_load(b));
+    else if (op == 1) r = C::template add<MC>(C::from_affine(pa), C::from_affine(C::aff_load(b)));
+    else if (op == 2) r = C::template dbl<MC>(C::from_affine(pa));
+    else if (op == 3) r = C::template mul_small<MC>(C::from_affine(pa), (uint32_t)b[0]);
+    else if (op == 4) {
+        typename C::X t = C::template dbl<MI>(C::from_affine(pa));  // 2a
+        t = C::template add_affine<MI>(t, pa);                      // 3a
+        const typename C::Affine na = C::aff_neg(pa);
+        t = C::template add_affine<MI>(t, na);                      // 2a
+        t = C::template add_affine<MI>(t, na);                      // a, ZZ != 1
+        r = C::template add_affine<MI>(t, C::aff_load(b));
+    } else if (op == 5) {
+        typename C::X t = C::template dbl<MC>(C::from_affine(pa));
+        t = C::template add_affine<MC>(t, C::aff_neg(pa));  // a, ZZ != 1
+        const typename C::Affine pb = C::aff_load(b);
+        typename C::X u = C::template dbl<MC>(C::from_affine(pb));
+        u = C::template add_affine<MC>(u, C::aff_neg(pb));  // b, ZZ != 1
+        r = C::template add<MC>(t, u);
+    }
+    C::aff_store(out, C::to_affine(r));
+}
+// The whole multi-exponentiation through msm_enqueue on the host executor.  out as the device writes it (2 * AFF_WORDS words);
+// returns the error flag, or -1 when the plan does not fit.  reverse != 0 runs every launch's threads in descending order.
+template <class C>
+int g_msm(const uint64_t* points, const uint64_t* scalars, size_t n, int scalars_mont, int c_force, int t_force, int reverse, uint64_t* out,
+          uint32_t* plan_out) {
     if (n == 0) {
-        memset(out16, 0, 128);
+        memset(out, 0, 2 * C::AFF_WORDS * 8);
         return 0;
     }
     const MsmPlan pl = msm_make_plan(n, scalars_mont, c_force, t_force);
     if (plan_out) plan_out[0] = pl.c, plan_out[1] = pl.W, plan_out[2] = pl.T, plan_out[3] = pl.L, plan_out[4] = pl.nchunks, plan_out[5] = (uint32_t)pl.max_tasks;
     if ((uint64_t)pl.n * pl.W >= 0xffffffffull) return -1;
-    const MsmWorkspace ws = msm_layout(pl);
+    const MsmWorkspace ws = msm_layout(pl, 8 * C::X_WORDS, 8 * C::AFF_WORDS);
     std::vector<unsigned char> buf(ws.bytes + 256, 0xA5);  // poisoned: nothing may rely on zero-initialised workspace
     unsigned char* base = (unsigned char*)(((uintptr_t)buf.data() + 255) & ~(uintptr_t)255);
-    int launches;
     if (reverse) {
         HostExecReverse ex;
-        launches = msm_enqueue(ex, pl, ws, base, points, scalars);
+        (void)msm_enqueue<C>(ex, pl, ws, base, points, scalars);
     } else {
         HostExec ex;
-        launches = msm_enqueue(ex, pl, ws, base, points, scalars);
+        (void)msm_enqueue<C>(ex, pl, ws, base, points, scalars);
     }
-    (void)launches;
-    memcpy(out16, base + ws.out, 128);
+    memcpy(out, base + ws.out, 2 * C::AFF_WORDS * 8);
     uint32_t flag;
     memcpy(&flag, base + ws.err, 4);
     return (int)flag;
 }
+}  // namespace
 
-void emu_g1_add_affine(const uint64_t* a, const uint64_t* b, uint64_t* out16) { KAddAffine::run(0, a, b, out16); }
+extern "C" {
+void emu_g1_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) { g_op<G1>(op, a, b, out); }
+void emu_g2_op(int op, const uint64_t* a, const uint64_t* b, uint64_t* out) { g_op<G2>(op, a, b, out); }
+int emu_msm(const uint64_t* points, const uint64_t* scalars, size_t n, int scalars_mont, int c_force, int t_force, int reverse, uint64_t* out16,
+            uint32_t* plan_out) {
+    return g_msm<G1>(points, scalars, n, scalars_mont, c_force, t_force, reverse, out16, plan_out);
+}
+int emu_g2_msm(const uint64_t* points, const uint64_t* scalars, size_t n, int scalars_mont, int c_force, int t_force, int reverse, uint64_t* out32,
+               uint32_t* plan_out) {
+    return g_msm<G2>(points, scalars, n, scalars_mont, c_force, t_force, reverse, out32, plan_out);
+}
+void emu_g1_add_affine(const uint64_t* a, const uint64_t* b, uint64_t* out16) { KAddAffine<G1>::run(0, a, b, out16); }
+void emu_g2_add_affine(const uint64_t* a, const uint64_t* b, uint64_t* out32) { KAddAffine<G2>::run(0, a, b, out32); }
+// Fp2 (fptower.E2) operations: op 0 mul (inlined base multiplier), 1 sqr, 2 add, 3 sub, 4 inv, 5 mul (out-of-line base multiplier)
+void emu_fp2_op(int op, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+    for (size_t i = 0; i < n; i++) {
+        const Fp2El x = Fp2Base::load(a + 8 * i), y = b ? Fp2Base::load(b + 8 * i) : Fp2Base::zero();
+        Fp2El r = Fp2Base::zero();
+        switch (op) {
+            case 0: r = Fp2Mul<FpMulInline>::mul(x, y); break;
+            case 1: r = Fp2Mul<FpMulInline>::sqr(x); break;
+            case 2: r = Fp2Base::add(x, y); break;
+            case 3: r = Fp2Base::sub(x, y); break;
+            case 4: r = Fp2Base::inv(x); break;
+            case 5: r = Fp2Mul<FpMulCall>::mul(x, y); break;
+        }
+        Fp2Base::store(out + 8 * i, r);
+    }
+}
 }  // extern "C"
 
 // ---- FFT -----------------------------------------------------------------------------------------------------------------------

@@ -39,13 +39,14 @@ def cmsm():
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [EMU_SRC] + [os.path.join(EC_DIR, f) for f in ("field.cuh", "g1.cuh", "msm.cuh")]
+    deps = [EMU_SRC] + [os.path.join(EC_DIR, f) for f in ("field.cuh", "curve.cuh", "msm.cuh")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
         os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-Werror", "-Wno-unknown-pragmas",
                                "-o", EMU_SO, EMU_SRC])
     L = ctypes.CDLL(EMU_SO)
     L.emu_msm.restype = ctypes.c_int
+    L.emu_g2_msm.restype = ctypes.c_int
     return L
 
 
@@ -168,7 +169,7 @@ def test_emulated_field_ops_match_big_integers(cmsm, emu):
 
 
 def test_emulated_group_law_handles_every_exceptional_case(cmsm, emu):
-    """madd-2008-s / add-2008-s / dbl-2008-s-1 of csrc/ec/g1.cuh against the oracle's affine law: generic, P + P, P + (-P),
+    """madd-2008-s / add-2008-s / dbl-2008-s-1 of csrc/ec/curve.cuh on G1 against the oracle's affine law: generic, P + P, P + (-P),
     infinity on either side, on trivial (ZZ = 1) and non-trivial representations, inlined and out-of-line multiplier"""
     pts = cmsm.gen_points(6)
     zero = np.zeros(8, dtype=np.uint64)
@@ -276,6 +277,103 @@ def test_plan_invariants(emu):
         B = 1 << (c - 1)
         assert L * nch >= B and L * (nch - 1) < B
         assert not out.any()  # 0 * P = infinity
+
+
+# ------------------------------------------------------------------------------------------------ 2b. G2 (prove.go:277, Bs)
+def test_oracle_g2_known_answers(cmsm):
+    """the published generator of G2 (EIP-197 / gnark-crypto) lies on y^2 = x^3 + 3/(9+u) and has order q; C oracle == Python"""
+    import pyref_msm as pr
+    assert pr.g2_is_on_curve(pr.G2) and pr.g2_mul(pr.Q, pr.G2) == pr.INF2 and pr.g2_mul(pr.Q - 1, pr.G2) == pr.g2_neg(pr.G2)
+    g = cmsm.g2_generator()
+    assert cmsm.g2_point_to_ints(g) == pr.G2 and cmsm.g2_is_on_curve(g)
+    bad = g.copy()
+    bad[0] ^= np.uint64(1)
+    assert not cmsm.g2_is_on_curve(bad)
+    assert cmsm.g2_point_to_ints(cmsm.g2_add(g, g)) == pr.g2_add(pr.G2, pr.G2)
+    assert cmsm.g2_point_to_ints(cmsm.g2_scalar_mul(g, pr.Q - 1)) == pr.g2_neg(pr.G2)
+    assert not cmsm.g2_add(g, cmsm.g2_neg(g)).any()
+    rng = random.Random(3)
+    n = 10
+    pts = cmsm.g2_gen_points(n)
+    ints = [cmsm.g2_point_to_ints(p) for p in pts]
+    assert ints[3] == pr.g2_mul(0x7654321 + 3 * 0xD1B54A32D192ED03, pr.G2) and all(pr.g2_is_on_curve(p) for p in ints)
+    sc = [0, 1, pr.Q - 1] + [rng.randrange(pr.Q) for _ in range(n - 3)]
+    want = pr.g2_multi_exp(ints, sc)
+    assert cmsm.g2_point_to_ints(cmsm.g2_multiexp(pts, cmsm.scalars_regular(sc))) == want
+    assert cmsm.g2_point_to_ints(cmsm.g2_multiexp(pts, cmsm.scalars_mont(sc), mont=True)) == want
+
+
+def test_emulated_fp2_ops_match_big_integers(cmsm, emu):
+    """fptower.E2 as the kernels compute it (Karatsuba product, complex squaring, norm inversion) against the schoolbook definition"""
+    import pyref_msm as pr
+    P, RP, RI = cmsm.P, cmsm.RP, cmsm.RP_INV
+    rng = random.Random(5)
+    e = [0, 1, P - 1, P - 2, RP, (1 << 253) - 1, P >> 1]
+    vals = [(x, y) for x in e for y in e] + [(rng.randrange(P), rng.randrange(P)) for _ in range(300)]
+    vb = list(reversed(vals))
+    tom = lambda vs: np.array([cmsm.limbs(v[0] * RP % P) + cmsm.limbs(v[1] * RP % P) for v in vs], dtype=np.uint64)
+    frm = lambda arr: [(cmsm.unlimbs(r[:4]) * RI % P, cmsm.unlimbs(r[4:]) * RI % P) for r in arr]
+    a, b = tom(vals), tom(vb)
+    out = np.zeros_like(a)
+    ops = {0: pr.f2_mul, 5: pr.f2_mul, 1: lambda x, y: pr.f2_mul(x, x), 2: pr.f2_add, 3: pr.f2_sub,
+           4: lambda x, y: pr.f2_inv(x) if x != (0, 0) else (0, 0)}
+    for op, f in ops.items():
+        k = len(vals) if op != 4 else 80
+        emu.emu_fp2_op(op, _p(a), _p(b), ctypes.c_size_t(k), _p(out))
+        assert frm(out[:k]) == [f(x, y) for x, y in zip(vals[:k], vb[:k])], op
+
+
+def test_emulated_g2_group_law_handles_every_exceptional_case(cmsm, emu):
+    pts = cmsm.g2_gen_points(6)
+    zero = np.zeros(16, dtype=np.uint64)
+    g = cmsm.g2_generator()
+    cases = [(pts[0], pts[1]), (pts[2], pts[2]), (pts[3], cmsm.g2_neg(pts[3])), (zero, pts[4]), (pts[4], zero), (zero, zero), (g, g), (g, cmsm.g2_neg(g))]
+    out = np.zeros(16, dtype=np.uint64)
+    out32 = np.zeros(32, dtype=np.uint64)
+    for a, b in cases:
+        want = cmsm.g2_add(a, b)
+        for op in (0, 1, 4, 5):
+            if op in (4, 5) and (not a.any() or (op == 5 and not b.any())):
+                continue
+            emu.emu_g2_op(op, _p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out))
+            assert np.array_equal(out, want), op
+            assert cmsm.g2_is_on_curve(out)
+        emu.emu_g2_add_affine(_p(np.ascontiguousarray(a)), _p(np.ascontiguousarray(b)), _p(out32))
+        assert np.array_equal(out32[:16], want)
+        (x0, x1), (y0, y1) = cmsm.g2_point_to_ints(want)
+        assert [cmsm.unlimbs(out32[16 + 4 * k:20 + 4 * k]) for k in range(4)] == [x0, x1, y0, y1]  # the regular-form copy
+    for a in (pts[0], g, zero):
+        emu.emu_g2_op(2, _p(np.ascontiguousarray(a)), _p(zero), _p(out))
+        assert np.array_equal(out, cmsm.g2_add(a, a))
+        for k in (0, 1, 2, 3, 255, 256, 0xFFFFFFFF):
+            kk = np.zeros(16, dtype=np.uint64)
+            kk[0] = k
+            emu.emu_g2_op(3, _p(np.ascontiguousarray(a)), _p(kk), _p(out))
+            assert np.array_equal(out, cmsm.g2_scalar_mul(a, k)), k
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 64, 300])
+def test_emulated_g2_multiexp_matches_oracle(cmsm, emu, n):
+    """the same launch sequence over the quadratic extension: G2Affine.MultiExp"""
+    rng = random.Random(300 + n)
+    pts = cmsm.g2_gen_points(n, a=rng.randrange(cmsm.Q), b=rng.randrange(cmsm.Q))
+    if n >= 7:
+        pts[1] = 0
+        pts[3] = pts[2]
+        pts[5] = cmsm.g2_neg(pts[4])
+    for name, vals in _scalar_sets(cmsm, n, rng):
+        if n > 64 and name in ("small", "digit boundaries"):
+            continue
+        reg = cmsm.scalars_regular(vals)
+        want = cmsm.g2_multiexp(pts, reg)
+        for c, T in ([(0, 0), (2, 0), (3, 1), (16, 0)] if n <= 64 else [(0, 0), (5, 3)]):
+            for rev in (0, 1):
+                out = np.zeros(32, dtype=np.uint64)
+                rc = emu.emu_g2_msm(_p(pts), _p(reg), ctypes.c_size_t(n), 0, c, T, rev, _p(out), None)
+                assert rc == 0 and np.array_equal(out[:16], want), (name, c, T, rev)
+        out = np.zeros(32, dtype=np.uint64)
+        rc = emu.emu_g2_msm(_p(pts), _p(cmsm.scalars_mont(vals)), ctypes.c_size_t(n), 1, 0, 0, 0, _p(out), None)
+        assert rc == 0 and np.array_equal(out[:16], want), name
 
 
 # ------------------------------------------------------------------------------------------------ 3. the library without a GPU

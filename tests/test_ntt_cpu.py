@@ -35,7 +35,7 @@ def cfft():
 
 @pytest.fixture(scope="module")
 def emu():
-    deps = [EMU_SRC] + [os.path.join(EC_DIR, f) for f in ("field.cuh", "g1.cuh", "msm.cuh", "ntt.cuh")]
+    deps = [EMU_SRC] + [os.path.join(EC_DIR, f) for f in ("field.cuh", "curve.cuh", "msm.cuh", "ntt.cuh")]
     if not os.path.exists(EMU_SO) or any(os.path.getmtime(d) > os.path.getmtime(EMU_SO) for d in deps):
         os.makedirs(os.path.dirname(EMU_SO), exist_ok=True)
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-Wextra", "-Werror", "-Wno-unknown-pragmas",

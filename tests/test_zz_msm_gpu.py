@@ -243,3 +243,67 @@ def test_multiexp_full_size_closed_form(cmsm, ecx, lg):
     print("multiexp 2^%d: window %d bits, %d windows, %.2f ms on the device, workspace %.0f MiB"
           % (lg, stats.last_c, stats.last_windows, stats.last_device_ms, stats.workspace_bytes / 2**20))
     ecx.SetBases(7, np.zeros((0, 8), dtype=np.uint64))
+
+
+# ------------------------------------------------------------------------------------------------ G2 (prove.go:277, Bs)
+def test_g2_add_on_the_device(cmsm, ecx):
+    pts = cmsm.g2_gen_points(6)
+    zero = np.zeros(16, dtype=np.uint64)
+    g = cmsm.g2_generator()
+    for a, b in [(pts[0], pts[1]), (pts[2], pts[2]), (pts[3], cmsm.g2_neg(pts[3])), (zero, pts[4]), (pts[4], zero), (zero, zero), (g, g),
+                 (g, cmsm.g2_neg(g))]:
+        assert np.array_equal(ecx.AddG2(a, b), cmsm.g2_add(a, b))
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 7, 64, 300, 4096])
+def test_g2_multiexp_matches_oracle(cmsm, ecx, n):
+    """G2Affine.MultiExp: the same kernels over Fp2 (16-word points), every scalar shape, forced plans, both scalar forms"""
+    from gkrb200 import ec
+    rng = random.Random(500 + n)
+    pts = cmsm.g2_gen_points(n, a=rng.randrange(cmsm.Q), b=rng.randrange(cmsm.Q))
+    if n >= 7:
+        pts[1] = 0
+        pts[3] = pts[2]
+        pts[5] = cmsm.g2_neg(pts[4])
+    ecx.SetBasesG2(9, pts)
+    try:
+        for name, vals in _scalar_sets(cmsm, n, rng):
+            reg, mont = cmsm.scalars_regular(vals), cmsm.scalars_mont(vals)
+            want = cmsm.g2_multiexp(pts, reg) if n else np.zeros(16, dtype=np.uint64)
+            for c, T in [(0, 0), (2, 0), (3, 1), (7, 2), (16, 0)]:
+                ecx.set_plan(c, T)
+                assert np.array_equal(ecx.MultiExpG2(9, reg), want), (name, c, T)
+            ecx.set_plan(0, 0)
+            assert np.array_equal(ecx.MultiExpG2(9, mont, ec.SCALARS_MONTGOMERY), want), name
+            assert np.array_equal(ecx.MultiExpPointsG2(pts, reg), want), name
+            if n:
+                assert cmsm.g2_is_on_curve(want)
+    finally:
+        ecx.set_plan(0, 0)
+    if n:
+        # a slot holds one kind of point
+        with pytest.raises(ec.GkrB200EcError) as e:
+            ecx.MultiExp(9, cmsm.scalars_regular([1]))
+        assert e.value.code == -1 and "G2" in str(e.value)
+    ecx.SetBasesG2(9, np.zeros((0, 16), dtype=np.uint64))
+
+
+def test_g2_multiexp_2pow20_closed_form(cmsm, ecx):
+    """2^20 points of G2 with a known discrete log: sum_i s_i P_i = (a sum s_i + b sum i s_i) G2gen, one scalar multiplication of the oracle"""
+    n = 1 << 20
+    a, b = 0x7654321, 0xD1B54A32D192ED03
+    q = cmsm.Q
+    pts = cmsm.g2_gen_points(n, a=a, b=b)
+    ecx.SetBasesG2(10, pts)
+    rng = np.random.default_rng(77)
+    s = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    s[:, 3] >>= np.uint64(12)
+    pyr = random.Random(20)
+    s[:1024] = cmsm.scalars_regular([pyr.randrange(q) for _ in range(1024)])
+    tot, wtot = _limb_sums(s)
+    got = ecx.MultiExpG2(10, s)
+    assert np.array_equal(got, cmsm.g2_scalar_mul(cmsm.g2_generator(), (a * tot + b * wtot) % q))
+    assert cmsm.g2_is_on_curve(got)
+    st = ecx.stats()
+    print("G2 multiexp 2^20: window %d bits, %.2f ms on the device" % (st.last_c, st.last_device_ms))
+    ecx.SetBasesG2(10, np.zeros((0, 16), dtype=np.uint64))
