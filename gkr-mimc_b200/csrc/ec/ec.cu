@@ -10,6 +10,7 @@
 
 #include "../../../include/gkrb200_ec.h"
 #include "msm.cuh"
+#include "groth16.hpp"
 #include "ntt.cuh"
 
 namespace {
@@ -589,6 +590,64 @@ int gkrb200ec_compute_h(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, 
     c->st.h2d_bytes += 3 * n_in * 32;
     if (h_out) c->st.d2h_bytes += n * 32;
     if (d_h_out) *d_h_out = v[0];
+    return 0;
+}
+
+// ---- ComputeGroth16Proof ------------------------------------------------------------------------------------------------------
+namespace {
+struct CudaGroth16Ops {
+    gkrb200ec_ctx* c;
+    const gkrb200ec_groth16_pk* pk;
+    const uint64_t *a, *b, *cc;
+    size_t n_constraints;
+    const uint64_t *wa, *wb;
+    size_t na, nb;
+    int form;
+    const void* d_h = nullptr;
+    const uint64_t* alpha() const { return pk->g1_alpha; }
+    const uint64_t* beta() const { return pk->g1_beta; }
+    const uint64_t* delta() const { return pk->g1_delta; }
+    const uint64_t* beta2() const { return pk->g2_beta; }
+    const uint64_t* delta2() const { return pk->g2_delta; }
+    int smul_g1(const uint64_t* pt, const uint64_t* k_regular, uint64_t* out) { return multiexp_points<ec::G1>(c, pt, k_regular, 1, GKRB200EC_SCALARS_REGULAR, out); }
+    int smul_g2(const uint64_t* pt, const uint64_t* k_regular, uint64_t* out) { return multiexp_points<ec::G2>(c, pt, k_regular, 1, GKRB200EC_SCALARS_REGULAR, out); }
+    int add_g1(const uint64_t* x, const uint64_t* y, uint64_t* out) {
+        uint64_t r[2 * ec::G1::AFF_WORDS];
+        if (const int rc = add_points<ec::G1>(c, x, y, r)) return rc;
+        memcpy(out, r, ec::G1::AFF_WORDS * 8);
+        return 0;
+    }
+    int add_g2(const uint64_t* x, const uint64_t* y, uint64_t* out) {
+        uint64_t r[2 * ec::G2::AFF_WORDS];
+        if (const int rc = add_points<ec::G2>(c, x, y, r)) return rc;
+        memcpy(out, r, ec::G2::AFF_WORDS * 8);
+        return 0;
+    }
+    int compute_h() { return gkrb200ec_compute_h(c, a, b, cc, n_constraints, nullptr, &d_h); }
+    int msm_g1(int which, uint64_t* out) {  // 0: pk.G1.A x wireValuesA, 1: pk.G1.B x wireValuesB
+        return which == 0 ? multiexp_host<ec::G1>(c, pk->slot_g1_a, wa, na, form, out) : multiexp_host<ec::G1>(c, pk->slot_g1_b, wb, nb, form, out);
+    }
+    int msm_g1_h(uint64_t* out) {  // pk.G1.Z x h, h read where computeH left it (regular form)
+        return multiexp_device<ec::G1>(c, pk->slot_g1_z, d_h, (size_t)1 << c->dom.log_n, GKRB200EC_SCALARS_REGULAR, out);
+    }
+    int msm_g2(uint64_t* out) { return multiexp_host<ec::G2>(c, pk->slot_g2_b, wb, nb, form, out); }
+};
+}  // namespace
+
+int gkrb200ec_groth16_prove(gkrb200ec_ctx* c, const gkrb200ec_groth16_pk* pk, const uint64_t* a, const uint64_t* b, const uint64_t* cc, size_t n_constraints,
+                            const uint64_t* wa, size_t na, const uint64_t* wb, size_t nb, int form, const uint64_t* r, const uint64_t* s, uint64_t* ar_out,
+                            uint64_t* bs_out, uint64_t* krs_out) {
+    if (!c || !pk || !r || !s || !ar_out || !bs_out || !krs_out) return fail(GKRB200EC_ERR_ARG, "null pointer");
+    if (!pk->g1_alpha || !pk->g1_beta || !pk->g1_delta || !pk->g2_beta || !pk->g2_delta) return fail(GKRB200EC_ERR_ARG, "null proving-key point");
+    if (!c->have_domain) return fail(GKRB200EC_ERR_ARG, "no fft domain: call gkrb200ec_fft_domain_init first");
+    if (const int rc = check_slot(c, pk->slot_g1_z, (size_t)1 << c->dom.log_n, ec::G1::AFF_WORDS)) return rc;  // len(pk.G1.Z) == domain.Cardinality
+    if (!ec::f_is_canonical<ec::FrMod>(ec::big_load(r)) || !ec::f_is_canonical<ec::FrMod>(ec::big_load(s))) return fail(GKRB200EC_ERR_ARG, "r or s is not a reduced fr.Element");
+    CudaGroth16Ops ops{c, pk, a, b, cc, n_constraints, wa, wb, na, nb, form};
+    ec::Groth16Out out;
+    if (const int rc = ec::groth16_compose(ops, r, s, out)) return rc;
+    memcpy(ar_out, out.ar, sizeof out.ar);
+    memcpy(bs_out, out.bs, sizeof out.bs);
+    memcpy(krs_out, out.krs, sizeof out.krs);
     return 0;
 }
 

@@ -11,6 +11,7 @@
     fft.NewDomain(m, 1, true) (groth16/setup.go:98)                        EcContext.NewDomain(m)
     domain.FFT(a, fft.DIT|DIF, coset) / domain.FFTInverse                  EcContext.FFT(a, decimation, coset) / FFTInverse
     computeH(a, b, c, &pk.Domain) (prove.go:310-366)                       EcContext.ComputeH(a, b, c) / ComputeHDevice
+    ComputeGroth16Proof(r1cs, pk, a, b, c, wireValues) (prove.go:100-306)  EcContext.ComputeGroth16Proof(...) (r, s from the caller)
 
 Points are numpy uint64 arrays (..., 8) = []bn254.G1Affine (X, Y; Montgomery; infinity all zero), scalars (..., 4) = []fr.Element.
 Everything that touches a point array runs on the GPU; the library fails loudly without one.  There is no CPU fallback.
@@ -45,6 +46,13 @@ class EcStats(ctypes.Structure):
         ("fft_calls", ctypes.c_uint64),
         ("last_fft_device_ms", ctypes.c_double),
     ]
+
+
+class Groth16Pk(ctypes.Structure):
+    """gkrb200ec_groth16_pk: which slots hold pk.G1.A / pk.G1.B / pk.G1.Z / pk.G2.B, and the five single points of the key"""
+    _fields_ = [("slot_g1_a", ctypes.c_int), ("slot_g1_b", ctypes.c_int), ("slot_g1_z", ctypes.c_int), ("slot_g2_b", ctypes.c_int),
+                ("g1_alpha", ctypes.c_void_p), ("g1_beta", ctypes.c_void_p), ("g1_delta", ctypes.c_void_p),
+                ("g2_beta", ctypes.c_void_p), ("g2_delta", ctypes.c_void_p)]
 
 
 class GkrB200EcError(RuntimeError):
@@ -91,6 +99,7 @@ def lib():
     L.gkrb200ec_fft.argtypes = [vp, vp, sz, i32, i32]
     L.gkrb200ec_fft_inverse.argtypes = [vp, vp, sz, i32, i32]
     L.gkrb200ec_compute_h.argtypes = [vp, vp, vp, vp, sz, vp, ctypes.POINTER(vp)]
+    L.gkrb200ec_groth16_prove.argtypes = [vp, ctypes.POINTER(Groth16Pk), vp, vp, vp, sz, vp, sz, vp, sz, i32, vp, vp, vp, vp, vp]
     L.gkrb200ec_get_stats.argtypes = [vp, ctypes.POINTER(EcStats)]
     _lib = L
     return L
@@ -292,6 +301,25 @@ class EcContext:
         check(lib().gkrb200ec_compute_h(self._h, _p(a) if n_in else None, _p(b) if n_in else None, _p(c) if n_in else None, n_in, None,
                                         ctypes.byref(ptr)))
         return ptr.value
+
+    def ComputeGroth16Proof(self, slots, points, a, b, c, wire_values_a, wire_values_b, r, s, form=SCALARS_REGULAR):
+        """ComputeGroth16Proof(r1cs, pk, a, b, c, wireValues) (prover/gadget/prove.go:100-306) with the caller's r, s.
+        slots = (slot of pk.G1.A, pk.G1.B, pk.G1.Z, pk.G2.B); points = dict g1_alpha, g1_beta, g1_delta (8,), g2_beta, g2_delta (16,);
+        r, s: (4,) Montgomery fr.Element.  The context's fft domain must cover the constraints.  -> (Ar (8,), Bs (16,), Krs (8,))"""
+        a, b, c = (fr_array(v).reshape(-1, 4) for v in (a, b, c))
+        wa, wb = fr_array(wire_values_a).reshape(-1, 4), fr_array(wire_values_b).reshape(-1, 4)
+        if not (a.shape == b.shape == c.shape):
+            raise ValueError("a, b, c must have the same length")
+        keep = {k: g1_array(points[k]).reshape(8) for k in ("g1_alpha", "g1_beta", "g1_delta")}
+        keep.update({k: g2_array(points[k]).reshape(16) for k in ("g2_beta", "g2_delta")})
+        pk = Groth16Pk(slots[0], slots[1], slots[2], slots[3], *[keep[k].ctypes.data for k in ("g1_alpha", "g1_beta", "g1_delta", "g2_beta", "g2_delta")])
+        r, s = fr_array(r).reshape(4), fr_array(s).reshape(4)
+        ar, bs, krs = np.zeros(8, dtype=np.uint64), np.zeros(16, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+        n = a.shape[0]
+        check(lib().gkrb200ec_groth16_prove(self._h, ctypes.byref(pk), _p(a) if n else None, _p(b) if n else None, _p(c) if n else None, n,
+                                            _p(wa) if wa.shape[0] else None, wa.shape[0], _p(wb) if wb.shape[0] else None, wb.shape[0], form,
+                                            _p(r), _p(s), _p(ar), _p(bs), _p(krs)))
+        return ar, bs, krs
 
     def set_plan(self, window_bits=0, task_size=0):
         check(lib().gkrb200ec_set_plan(self._h, window_bits, task_size))

@@ -119,6 +119,28 @@ int gkrb200ec_fft_inverse(gkrb200ec_ctx *ctx, uint64_t *a, size_t n, int decimat
 int gkrb200ec_compute_h(gkrb200ec_ctx *ctx, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t n_in, uint64_t *h_out,
                         const void **d_h_out);
 
+/* ---- ComputeGroth16Proof (prover/gadget/prove.go:100-306) in one call -------------------------------------------------------
+ * The proving key's point arrays are resident base slots (uploaded once with gkrb200ec_g1_set_bases / gkrb200ec_g2_set_bases,
+ * infinity-filtered exactly as groth16.ProvingKey holds pk.G1.A, pk.G1.B, pk.G2.B; pk.G1.Z whole and bit-reversed as setup.go:229
+ * leaves it); a fft domain for the constraint count must be set (gkrb200ec_fft_domain_init).
+ *   h   = computeH(a, b, c)                                                        prove.go:126
+ *   ar  = MultiExp(pk.G1.A, wireValuesA) + pk.G1.Alpha + r * pk.G1.Delta            prove.go:199-210  -> proof.Ar
+ *   bs1 = MultiExp(pk.G1.B, wireValuesB) + pk.G1.Beta  + s * pk.G1.Delta            prove.go:186-196
+ *   krs = -(r s) * pk.G1.Delta + MultiExp(pk.G1.Z, h) + s * ar + r * bs1            prove.go:212-262  -> grothProof.Krs (the fork
+ *         removed the pk.G1.K term, :224-231; the caller adds KrsPrivNotGkr, :94)
+ *   bs  = MultiExp(pk.G2.B, wireValuesB) + s * pk.G2.Delta + pk.G2.Beta             prove.go:265-292  -> proof.Bs
+ * r, s: fr.Element (Montgomery) sampled by the caller -- prove.go:154-161 draws them with SetRandom, which stays in Go; with them
+ * given, the outputs are a deterministic function of the inputs (and bit-exact with the reference for the same r, s).
+ * wire_values_a / wire_values_b: the filtered wire values (prove.go:136-157), in `scalar_form`; a, b, c: solution.A/B/C, Montgomery. */
+typedef struct {
+    int slot_g1_a, slot_g1_b, slot_g1_z, slot_g2_b;
+    const uint64_t *g1_alpha, *g1_beta, *g1_delta; /* 8 words each */
+    const uint64_t *g2_beta, *g2_delta;            /* 16 words each */
+} gkrb200ec_groth16_pk;
+int gkrb200ec_groth16_prove(gkrb200ec_ctx *ctx, const gkrb200ec_groth16_pk *pk, const uint64_t *a, const uint64_t *b, const uint64_t *c,
+                            size_t n_constraints, const uint64_t *wire_values_a, size_t n_a, const uint64_t *wire_values_b, size_t n_b,
+                            int scalar_form, const uint64_t *r, const uint64_t *s, uint64_t *ar_out, uint64_t *bs_out, uint64_t *krs_out);
+
 /* Tuning / test hooks: force the window width c (2..16, 0 = cost model) and the accumulation task size (0 = twice the mean
  * bucket load).  The result never depends on them.                                                                             */
 int gkrb200ec_set_plan(gkrb200ec_ctx *ctx, int window_bits, int task_size);

@@ -13,6 +13,7 @@
 
 #include "../../gkr-mimc_b200/csrc/ec/msm.cuh"
 #include "../../gkr-mimc_b200/csrc/ec/ntt.cuh"
+#include "../../gkr-mimc_b200/csrc/ec/groth16.hpp"
 
 namespace {
 struct HostExec {
@@ -235,4 +236,85 @@ int emu_fft_domain(uint32_t log_n, uint64_t* out) {
     return 0;
 }
 uint32_t emu_ntt_rev(uint32_t x, uint32_t log_n) { return ec::ntt_rev(x, log_n); }
+
+// ---- ComputeGroth16Proof: the product's sequencing (groth16.hpp) over the emulated kernels ------------------------------------------
+struct EmuGroth16In {
+    const uint64_t *g1_a, *g1_b, *g1_z, *g2_b;      // base arrays: n_a, n_b, cardinality, n_b points
+    const uint64_t *alpha, *beta, *delta, *beta2, *delta2;
+    const uint64_t *a, *b, *c;                      // n_constraints Montgomery elements each
+    const uint64_t *wa, *wb;                        // n_a / n_b scalars
+    uint64_t n_constraints, n_a, n_b;
+    uint32_t log_n;
+    int scalars_mont;
+};
+}  // extern "C"
+namespace {
+struct EmuGroth16Ops {
+    const EmuGroth16In& in;
+    std::vector<uint64_t> h;
+    const uint64_t* alpha() const { return in.alpha; }
+    const uint64_t* beta() const { return in.beta; }
+    const uint64_t* delta() const { return in.delta; }
+    const uint64_t* beta2() const { return in.beta2; }
+    const uint64_t* delta2() const { return in.delta2; }
+    int smul_g1(const uint64_t* pt, const uint64_t* k, uint64_t* out) {
+        uint64_t r[16];
+        const int rc = g_msm<G1>(pt, k, 1, 0, 0, 0, 0, r, nullptr);
+        memcpy(out, r, 64);
+        return rc;
+    }
+    int smul_g2(const uint64_t* pt, const uint64_t* k, uint64_t* out) {
+        uint64_t r[32];
+        const int rc = g_msm<G2>(pt, k, 1, 0, 0, 0, 0, r, nullptr);
+        memcpy(out, r, 128);
+        return rc;
+    }
+    int add_g1(const uint64_t* x, const uint64_t* y, uint64_t* out) {
+        uint64_t r[16];
+        KAddAffine<G1>::run(0, x, y, r);
+        memcpy(out, r, 64);
+        return 0;
+    }
+    int add_g2(const uint64_t* x, const uint64_t* y, uint64_t* out) {
+        uint64_t r[32];
+        KAddAffine<G2>::run(0, x, y, r);
+        memcpy(out, r, 128);
+        return 0;
+    }
+    int compute_h() {
+        h.assign(4 * ((size_t)1 << in.log_n), 0);
+        return emu_compute_h(in.a, in.b, in.c, in.n_constraints, in.log_n, 0, h.data()) > 0 ? 0 : -1;
+    }
+    int msm_g1(int which, uint64_t* out) {
+        uint64_t r[16];
+        const int rc = which == 0 ? g_msm<G1>(in.g1_a, in.wa, in.n_a, in.scalars_mont, 0, 0, 0, r, nullptr)
+                                  : g_msm<G1>(in.g1_b, in.wb, in.n_b, in.scalars_mont, 0, 0, 1, r, nullptr);
+        memcpy(out, r, 64);
+        return rc;
+    }
+    int msm_g1_h(uint64_t* out) {
+        uint64_t r[16];
+        const int rc = g_msm<G1>(in.g1_z, h.data(), (size_t)1 << in.log_n, 0, 0, 0, 0, r, nullptr);
+        memcpy(out, r, 64);
+        return rc;
+    }
+    int msm_g2(uint64_t* out) {
+        uint64_t r[32];
+        const int rc = g_msm<G2>(in.g2_b, in.wb, in.n_b, in.scalars_mont, 0, 0, 0, r, nullptr);
+        memcpy(out, r, 128);
+        return rc;
+    }
+};
+}  // namespace
+extern "C" {
+int emu_groth16(const EmuGroth16In* in, const uint64_t* r, const uint64_t* s, uint64_t* ar, uint64_t* bs, uint64_t* krs) {
+    EmuGroth16Ops ops{*in, {}};
+    ec::Groth16Out out;
+    const int rc = ec::groth16_compose(ops, r, s, out);
+    if (rc) return rc;
+    memcpy(ar, out.ar, 64);
+    memcpy(bs, out.bs, 128);
+    memcpy(krs, out.krs, 64);
+    return 0;
+}
 }
