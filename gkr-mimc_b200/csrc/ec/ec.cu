@@ -29,6 +29,11 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(e_ == cudaErrorMemoryAllocation ? GKRB200EC_ERR_OOM : GKRB200EC_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); \
     } while (0)
 
+// The executor: every kernel body K::run(index, args...) of msm.cuh / ntt.cuh as a grid of 128-thread blocks on the context's stream.
+// (Test seam: tests/emu/ec_hostbuild.cpp compiles THIS FILE with g++ against a stand-in for the CUDA runtime and supplies its own
+// executor, so that the driver below -- staging, workspaces, slots, error paths, the Groth16 sequencing -- is exercised on the CPU
+// through the same C ABI.  The shipped library is built by nvcc and contains only the executor below.)
+#ifndef GKRB200EC_TEST_EXECUTOR
 template <class K, class... A>
 __global__ void __launch_bounds__(128) k_each(size_t n, A... a) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,6 +57,7 @@ struct CudaExec {
         if (e != cudaSuccess && err == cudaSuccess) err = e;
     }
 };
+#endif
 
 }  // namespace
 

@@ -64,14 +64,8 @@ class GkrB200EcError(RuntimeError):
 _lib = None
 
 
-def lib():
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(SO_PATH):
-        raise RuntimeError("gkrb200: %s is missing. Build it with `make -C %s` (or __graft_entry__.build()); there is no CPU fallback."
-                           % (SO_PATH, ROOT))
-    L = ctypes.CDLL(SO_PATH)
+def _bind(L):
+    """argument types of every entry point of include/gkrb200_ec.h"""
     vp, sz, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
     L.gkrb200ec_version.restype = ctypes.c_char_p
     L.gkrb200ec_last_error.restype = ctypes.c_char_p
@@ -101,8 +95,18 @@ def lib():
     L.gkrb200ec_compute_h.argtypes = [vp, vp, vp, vp, sz, vp, ctypes.POINTER(vp)]
     L.gkrb200ec_groth16_prove.argtypes = [vp, ctypes.POINTER(Groth16Pk), vp, vp, vp, sz, vp, sz, vp, sz, i32, vp, vp, vp, vp, vp]
     L.gkrb200ec_get_stats.argtypes = [vp, ctypes.POINTER(EcStats)]
-    _lib = L
     return L
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError("gkrb200: %s is missing. Build it with `make -C %s` (or __graft_entry__.build()); there is no CPU fallback."
+                           % (SO_PATH, ROOT))
+    _lib = _bind(ctypes.CDLL(SO_PATH))
+    return _lib
 
 
 def check(rc):
