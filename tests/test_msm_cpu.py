@@ -279,6 +279,43 @@ def test_plan_invariants(emu):
         assert not out.any()  # 0 * P = infinity
 
 
+def test_emulated_multiexp_randomised_sweep(cmsm, emu):
+    """80 random cases: size, window width, task size, scalar shape (incl. values on every signed-digit boundary of the chosen width),
+    scalar form, launch order, bases drawn with repetition and with infinity / negated points mixed in"""
+    rng = random.Random(2026)
+    q = cmsm.Q
+    pool = cmsm.gen_points(300, a=rng.randrange(q), b=rng.randrange(q))
+    for case in range(80):
+        n = rng.randrange(1, rng.choice([2, 3, 5, 17, 33, 100, 257]) + 1)
+        c = rng.choice([0, 0, 2, 3, 4, 5, 6, 8, 9, 12, 13, 15, 16])
+        T = rng.choice([0, 0, 1, 2, 3, 5, 16, 100])
+        kind = rng.randrange(6)
+        if kind == 0:
+            vals = [rng.randrange(q) for _ in range(n)]
+        elif kind == 1:
+            vals = [rng.randrange(1 << rng.choice([1, 8, 31, 32, 33, 64, 128, 253])) for _ in range(n)]
+        elif kind == 2:
+            vals = [rng.choice([0, 1, q - 1, q - 2, 1 << 253, (1 << 253) - 1, q >> 1]) for _ in range(n)]
+        elif kind == 3:
+            vals = [rng.randrange(q)] * n
+        elif kind == 4:
+            cc = max(c, 2)
+            vals = [((1 << (cc - 1)) * sum(1 << (cc * w) for w in range(254 // cc)) + rng.randrange(3) - 1) % q for _ in range(n)]
+        else:
+            vals = [(q - rng.randrange(1 << 20)) % q for _ in range(n)]
+        pts = pool[[rng.randrange(300) for _ in range(n)]].copy()
+        for j in range(n):
+            r = rng.random()
+            if r < 0.05:
+                pts[j] = 0
+            elif r < 0.15:
+                pts[j] = cmsm.neg(pts[j])
+        mont = int(rng.random() < 0.3)
+        sc = (cmsm.scalars_mont if mont else cmsm.scalars_regular)(vals)
+        rc, out, _ = _emu_msm(emu, pts, sc, mont, c, T, rng.randrange(2))
+        assert rc == 0 and np.array_equal(out[:8], cmsm.multiexp(pts, cmsm.scalars_regular(vals))), (case, n, c, T, kind, mont)
+
+
 # ------------------------------------------------------------------------------------------------ 2b. G2 (prove.go:277, Bs)
 def test_oracle_g2_known_answers(cmsm):
     """the published generator of G2 (EIP-197 / gnark-crypto) lies on y^2 = x^3 + 3/(9+u) and has order q; C oracle == Python"""
