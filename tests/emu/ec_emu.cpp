@@ -5,7 +5,7 @@
 // 64-bit C++ with the semantics of the inline-PTX ones the device uses (those are exercised on the GPU by every GKR parity test).
 // tests/test_msm_cpu.py and tests/test_ntt_cpu.py drive this against the oracles, so the digit decomposition, counting sort, task
 // splitting, XYZZ formulas with all exceptional cases, window reduction, the in-register butterfly passes, coset scalings and the
-// drivers' launch sequences are checked without a GPU; tests/test_zz_msm_gpu.py and tests/test_zz_ntt_gpu.py then check the real
+// drivers' launch sequences are checked without a GPU; tests/test_zz2_msm_gpu.py and tests/test_zz1_ntt_gpu.py then check the real
 // library on the device against the same oracles.
 #include <cstdlib>
 #include <cstring>

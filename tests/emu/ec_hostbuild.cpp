@@ -5,7 +5,7 @@
 // immediate streams), and the executor -- the one piece of ec.cu that needs nvcc -- is replaced through its test seam by one that
 // runs every "launch" as a loop over thread indices (in descending order when EC_HOSTBUILD_REVERSE is set in the environment).
 // The result exports the same C ABI as libgkrb200ec.so, so tests/test_ec_driver_cpu.py runs the DEVICE parity tests' own bodies
-// (tests/test_zz_*_gpu.py) against it: staging, grow-only workspaces, base slots, error paths, statistics and the Groth16
+// (tests/test_zz*_gpu.py) against it: staging, grow-only workspaces, base slots, error paths, statistics and the Groth16
 // sequencing of the real driver are exercised without a GPU.  What it cannot show: the CUDA runtime's own behaviour, launch
 // configuration, the inline-PTX carry chains (fr_device.cuh; covered by the GKR GPU tests), and speed.
 #include <cuda_runtime.h>

@@ -1,5 +1,5 @@
 """The Groth16-side library's OWN host driver on the CPU (gkr-mimc_b200/csrc/ec/ec.cu compiled by tests/emu/ec_hostbuild.cpp against a
-stand-in for the CUDA runtime) driven by the DEVICE parity tests' own bodies (tests/test_zz_*_gpu.py), against the same oracles.
+stand-in for the CUDA runtime) driven by the DEVICE parity tests' own bodies (tests/test_zz*_gpu.py), against the same oracles.
 
 Why: libgkrb200ec.so was written after the round's GPU budget was spent.  The kernel bodies are checked by tests/test_msm_cpu.py /
 test_ntt_cpu.py / test_groth16_cpu.py; this file adds the ~700 lines of host driver around them -- staging buffers, grow-only
@@ -65,9 +65,9 @@ def ecx(host_driver):
     c.close()
 
 
-import test_zz_msm_gpu as gpu_msm  # noqa: E402  (the GPU tests' bodies; their module-level gpu mark does not travel with the functions)
-import test_zz_ntt_gpu as gpu_ntt  # noqa: E402
-import test_zz_zgroth16_gpu as gpu_g16  # noqa: E402
+import test_zz2_msm_gpu as gpu_msm  # noqa: E402  (the GPU tests' bodies; their module-level gpu mark does not travel with the functions)
+import test_zz1_ntt_gpu as gpu_ntt  # noqa: E402
+import test_zz3_groth16_gpu as gpu_g16  # noqa: E402
 
 
 def test_g1_add(cmsm, ecx):

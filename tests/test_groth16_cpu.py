@@ -1,6 +1,6 @@
 """CPU test of the ComputeGroth16Proof sequencing (gkr-mimc_b200/csrc/ec/groth16.hpp; prover/gadget/prove.go:100-306): the product's
 composition run over the emulated kernels (tests/emu/ec_emu.cpp) against the oracle's own composition of the oracle's own pieces
-(oracle/cgroth16.py).  tests/test_zz_zgroth16_gpu.py runs the same comparison through the C ABI on the device."""
+(oracle/cgroth16.py).  tests/test_zz3_groth16_gpu.py runs the same comparison through the C ABI on the device."""
 import ctypes
 import os
 import random

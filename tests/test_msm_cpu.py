@@ -9,7 +9,7 @@ Three layers, none of which needs a GPU:
      backwards; on the host the carry chains are plain C++, on the device they are the inline-PTX primitives of fr_device.cuh;
   3. libgkrb200ec.so loads, exports every symbol include/gkrb200_ec.h declares, its host-only entry points (RawBytes, legacy
      Keccak-256, DeriveRandomnessFromPoint) agree with the oracle, and the device entry points fail loudly without a GPU.
-tests/test_zz_msm_gpu.py is the device parity test proper.
+tests/test_zz2_msm_gpu.py is the device parity test proper.
 """
 import ctypes
 import os

@@ -6,7 +6,7 @@
   2. the product's kernel bodies and drivers (gkr-mimc_b200/csrc/ec/ntt.cuh: in-register radix-8 / 4 / 2 passes, DIF and DIT,
      coset scalings, the fused computeH pipeline, the domain tables) compiled for the host by tests/emu/ec_emu.cpp and run launch
      by launch, forwards and backwards, against the oracle.
-tests/test_zz_ntt_gpu.py is the device parity test.
+tests/test_zz1_ntt_gpu.py is the device parity test.
 """
 import ctypes
 import os
