@@ -448,6 +448,42 @@ def test_ec_header_is_valid_c99(tmp_path):
                            str(tmp_path / "t.o")])
 
 
+def test_plain_c_program_reproduces_keccak_kat_through_the_ec_library(tmp_path):
+    """the header and the library from C99, no Python in between: legacy Keccak-256("abc") and RawBytes of the generator (1, 2)"""
+    from gkrb200 import ec
+    src = tmp_path / "kat.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "gkrb200_ec.h"
+int main(void) {
+    uint8_t h[32], raw[64];
+    if (gkrb200ec_keccak256((const uint8_t *)"abc", 3, h) != GKRB200EC_OK) return 1;
+    for (int i = 0; i < 32; i++) printf("%02x", h[i]);
+    printf("\n");
+    /* (1, 2) in Montgomery form: R mod p, 2R mod p */
+    uint64_t g[8] = {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL,
+                     0xa6ba871b8b1e1b3aULL, 0x14f1d651eb8e167bULL, 0xccdd46def0f28c58ULL, 0x1c14ef83340fbe5eULL};
+    if (gkrb200ec_g1_raw_bytes(g, raw) != GKRB200EC_OK) return 2;
+    for (int i = 0; i < 64; i++) printf("%02x", raw[i]);
+    printf("\n");
+    if (gkrb200ec_g1_raw_bytes(NULL, raw) != GKRB200EC_ERR_ARG) return 3;
+    printf("%s\n", gkrb200ec_last_error());
+    return 0;
+}
+''')
+    exe = tmp_path / "kat"
+    lib_dir = os.path.dirname(ec.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L" + lib_dir,
+                           "-lgkrb200ec", "-Wl,-rpath," + lib_dir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.split("\n")
+    assert lines[0] == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"
+    assert lines[1] == "%064x%064x" % (1, 2)
+    assert "null" in lines[2]
+
+
 def test_ec_host_entry_points_match_oracle(cmsm):
     """RawBytes, legacy Keccak-256 and DeriveRandomnessFromPoint (hints.go:147-159) run on the host inside the product"""
     from gkrb200 import ec
