@@ -16,7 +16,8 @@
 //                 (madd-2008-s, 8 products + 2 squarings each) -- this is where the work is: n * W mixed additions.  Tasks, not
 //                 buckets, are the unit of parallelism, so a skewed input (the reference benchmark hashes ONE value 2^k times:
 //                 all scalars equal, one bucket per window holds everything) still spreads over the whole GPU.
-//   5. k_bucket   one thread per key: sum of its tasks' partial sums (one, usually)
+//   5. k_group    one thread per GROUP of at most 32 partial sums of one key; k_bucket: one thread per key: sum of its group sums
+//                 (one partial sum and one group, usually; thousands of partial sums for the hot buckets of a skewed input)
 //   6. k_chunk    per window, per chunk of L consecutive buckets: sum_b (b + 1) * S_b by the running-sum trick on the chunk plus
 //                 (first bucket index) * (chunk total)
 //   7. k_window   one thread per window: sum of its chunks;  k_final: one thread: Horner over the windows (c doublings each),
@@ -43,6 +44,8 @@ struct MsmPlan {
     uint32_t scalars_mont;  // 1: scalars arrive in Montgomery form (fr.Element memory); 0: regular form (what MultiExp takes)
     uint32_t scan_L;        // elements per scan thread
     uint64_t max_tasks;     // upper bound of the number of accumulation tasks
+    uint32_t G;             // partial sums per reduction group (second level of the bucket reduction)
+    uint64_t max_groups;    // upper bound of the number of groups
 };
 
 // cost model: W * (n mixed additions + ~3 mixed-addition equivalents per bucket for the reduction)
@@ -74,6 +77,8 @@ inline MsmPlan msm_make_plan(size_t n, int scalars_mont, int c_force = 0, int T_
     pl.scalars_mont = scalars_mont ? 1 : 0;
     pl.scan_L = 256;
     pl.max_tasks = ((uint64_t)n * pl.W) / pl.T + pl.nkeys;
+    pl.G = 32;
+    pl.max_groups = pl.max_tasks / pl.G + pl.nkeys;
     return pl;
 }
 
@@ -158,6 +163,9 @@ struct KScatter {  // i < n
 struct KTaskCount {  // k < nkeys
     static EC_HD void run(size_t k, MsmPlan pl, const uint32_t* count, uint32_t* tcount) { tcount[k] = (count[k] + pl.T - 1) / pl.T; }
 };
+struct KGroupCount {  // k < nkeys: groups of at most G partial sums
+    static EC_HD void run(size_t k, MsmPlan pl, const uint32_t* tcount, uint32_t* gcount) { gcount[k] = (tcount[k] + pl.G - 1) / pl.G; }
+};
 // exclusive prefix sum of in[0..n) into out[0..n], out[n] = total, in three steps over chunks of L elements
 struct KScanA {  // j < nch
     static EC_HD void run(size_t j, const uint32_t* in, uint32_t* part, uint32_t n, uint32_t L) {
@@ -224,14 +232,36 @@ struct KAccum {  // t < max_tasks
         C::x_store(partial + (size_t)C::X_WORDS * t, acc);
     }
 };
+// Second level: a key with many tasks (a skewed input: thousands of partial sums for one bucket) is reduced in groups of G by
+// one thread per GROUP, so that no single thread walks more than G partial sums here and (tasks of the key) / G group sums in KBucket.
+template <class C>
+struct KGroup {  // g < max_groups
+    static EC_HD void run(size_t g, MsmPlan pl, const uint32_t* toff, const uint32_t* goff, const uint64_t* partial, uint64_t* gsum) {
+        typedef typename C::MCall M;
+        if (g >= goff[pl.nkeys]) return;
+        uint32_t lo = 0, hi = pl.nkeys;  // largest key with goff[key] <= g
+        while (hi - lo > 1) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (goff[mid] <= g) lo = mid;
+            else hi = mid;
+        }
+        const uint32_t key = lo;
+        const size_t first = (size_t)toff[key] + (g - goff[key]) * (size_t)pl.G;
+        const size_t end_key = toff[key + 1];
+        const size_t last = first + pl.G < end_key ? first + pl.G : end_key;
+        typename C::X acc = C::x_load(partial + (size_t)C::X_WORDS * first);
+        for (size_t t = first + 1; t < last; t++) acc = C::template add<M>(acc, C::x_load(partial + (size_t)C::X_WORDS * t));
+        C::x_store(gsum + (size_t)C::X_WORDS * g, acc);
+    }
+};
 template <class C>
 struct KBucket {  // k < nkeys
-    static EC_HD void run(size_t k, const uint32_t* toff, const uint64_t* partial, uint64_t* bucket) {
+    static EC_HD void run(size_t k, const uint32_t* goff, const uint64_t* gsum, uint64_t* bucket) {
         typedef typename C::MCall M;
-        const uint32_t lo = toff[k], hi = toff[k + 1];
+        const uint32_t lo = goff[k], hi = goff[k + 1];
         typename C::X acc = C::x_inf();
-        if (hi > lo) acc = C::x_load(partial + (size_t)C::X_WORDS * lo);
-        for (uint32_t t = lo + 1; t < hi; t++) acc = C::template add<M>(acc, C::x_load(partial + (size_t)C::X_WORDS * t));
+        if (hi > lo) acc = C::x_load(gsum + (size_t)C::X_WORDS * lo);
+        for (uint32_t t = lo + 1; t < hi; t++) acc = C::template add<M>(acc, C::x_load(gsum + (size_t)C::X_WORDS * t));
         C::x_store(bucket + (size_t)C::X_WORDS * k, acc);
     }
 };
@@ -293,7 +323,7 @@ struct KAddAffine {  // one thread: out = a + b (G1Affine.Add, hints.go:184), sa
 
 // ---- workspace and driver -----------------------------------------------------------------------------------------------------
 struct MsmWorkspace {  // offsets into one device buffer
-    size_t count, off, cursor, tcount, toff, part, entries, partial, bucket, chunk_out, win, err, out, bytes;
+    size_t count, off, cursor, tcount, toff, gcount, goff, part, entries, partial, gsum, bucket, chunk_out, win, err, out, bytes;
 };
 inline size_t msm_align(size_t x) { return (x + 255) & ~(size_t)255; }
 inline MsmWorkspace msm_layout(const MsmPlan& pl, size_t x_bytes, size_t aff_bytes) {  // sizes of one XYZZ / affine image
@@ -307,9 +337,12 @@ inline MsmWorkspace msm_layout(const MsmPlan& pl, size_t x_bytes, size_t aff_byt
     ws.off = o, o = msm_align(o + 4 * (nk + 1));
     ws.tcount = o, o = msm_align(o + 4 * (nk + 1));
     ws.toff = o, o = msm_align(o + 4 * (nk + 1));
+    ws.gcount = o, o = msm_align(o + 4 * (nk + 1));
+    ws.goff = o, o = msm_align(o + 4 * (nk + 1));
     ws.part = o, o = msm_align(o + 4 * (nch + 1));
     ws.entries = o, o = msm_align(o + 4 * ((size_t)pl.n * pl.W + 1));
     ws.partial = o, o = msm_align(o + x_bytes * pl.max_tasks);
+    ws.gsum = o, o = msm_align(o + x_bytes * pl.max_groups);
     ws.bucket = o, o = msm_align(o + x_bytes * nk);
     ws.chunk_out = o, o = msm_align(o + x_bytes * (size_t)pl.W * pl.nchunks);
     ws.win = o, o = msm_align(o + x_bytes * pl.W);
@@ -329,9 +362,12 @@ int msm_enqueue(Exec& ex, const MsmPlan& pl, const MsmWorkspace& ws, unsigned ch
     uint32_t* off = (uint32_t*)(base + ws.off);
     uint32_t* tcount = (uint32_t*)(base + ws.tcount);
     uint32_t* toff = (uint32_t*)(base + ws.toff);
+    uint32_t* gcount = (uint32_t*)(base + ws.gcount);
+    uint32_t* goff = (uint32_t*)(base + ws.goff);
     uint32_t* part = (uint32_t*)(base + ws.part);
     uint32_t* entries = (uint32_t*)(base + ws.entries);
     uint64_t* partial = (uint64_t*)(base + ws.partial);
+    uint64_t* gsum = (uint64_t*)(base + ws.gsum);
     uint64_t* bucket = (uint64_t*)(base + ws.bucket);
     uint64_t* chunk_out = (uint64_t*)(base + ws.chunk_out);
     uint64_t* win = (uint64_t*)(base + ws.win);
@@ -350,7 +386,12 @@ int msm_enqueue(Exec& ex, const MsmPlan& pl, const MsmWorkspace& ws, unsigned ch
     launches += ex.template launch<KScanC>(nch, (const uint32_t*)tcount, toff, (const uint32_t*)part, nk, sl, nch);
     launches += ex.template launch<KAccum<C>>(pl.max_tasks, pl, d_points, (const uint32_t*)entries, (const uint32_t*)off, (const uint32_t*)count,
                                               (const uint32_t*)toff, partial);
-    launches += ex.template launch<KBucket<C>>(nk, (const uint32_t*)toff, (const uint64_t*)partial, bucket);
+    launches += ex.template launch<KGroupCount>(nk, pl, (const uint32_t*)tcount, gcount);
+    launches += ex.template launch<KScanA>(nch, (const uint32_t*)gcount, part, nk, sl);
+    launches += ex.template launch<KScanB>(1, part, nch);
+    launches += ex.template launch<KScanC>(nch, (const uint32_t*)gcount, goff, (const uint32_t*)part, nk, sl, nch);
+    launches += ex.template launch<KGroup<C>>(pl.max_groups, pl, (const uint32_t*)toff, (const uint32_t*)goff, (const uint64_t*)partial, gsum);
+    launches += ex.template launch<KBucket<C>>(nk, (const uint32_t*)goff, (const uint64_t*)gsum, bucket);
     launches += ex.template launch<KChunk<C>>((size_t)pl.W * pl.nchunks, pl, (const uint64_t*)bucket, chunk_out);
     launches += ex.template launch<KWindow<C>>(pl.W, pl, (const uint64_t*)chunk_out, win);
     launches += ex.template launch<KFinal<C>>(1, pl, (const uint64_t*)win, out);

@@ -251,6 +251,12 @@ def test_emulated_multiexp_larger_and_skewed(cmsm, emu):
     want = cmsm.multiexp(pts, same)
     rc, out, _ = _emu_msm(emu, pts, same, T=16, reverse=1)
     assert rc == 0 and np.array_equal(out[:8], want)
+    # task size 1: every hot bucket has 4 096 partial sums = 128 reduction groups of 32 (the second level of the bucket reduction)
+    rc, out, _ = _emu_msm(emu, pts, same, T=1)
+    assert rc == 0 and np.array_equal(out[:8], want)
+    three = cmsm.scalars_regular([(i % 3 + 5) * 0x123456789ABCDEF123456789 % cmsm.Q for i in range(n)])  # key / msg / out repeated: the hint's shape
+    rc, out, _ = _emu_msm(emu, pts, three, T=3, reverse=1)
+    assert rc == 0 and np.array_equal(out[:8], cmsm.multiexp(pts, three))
 
 
 def test_emulated_multiexp_rejects_unreduced_scalars(cmsm, emu):
