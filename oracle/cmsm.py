@@ -127,6 +127,16 @@ def multiexp(points, scalars, mont=False, nthreads=None):
     return out
 
 
+def multiexp_buckets(points, scalars, mont=False, nthreads=None):
+    """G1Affine.MultiExp by gnark-crypto's published algorithm (bucket method, one task per window): the CPU baseline and a fast second oracle"""
+    points, scalars = _c(points, 8).reshape(-1, 8), _c(scalars, 4).reshape(-1, 4)
+    assert points.shape[0] == scalars.shape[0]
+    out = np.zeros(8, dtype=np.uint64)
+    lib().orc_g1_multiexp_buckets(_p(points), _p(scalars), ctypes.c_size_t(points.shape[0]), ctypes.c_int(1 if mont else 0),
+                                  ctypes.c_int(nthreads or threads()), _p(out))
+    return out
+
+
 def gen_points(n, a=0x1234567, b=0x9E3779B97F4A7C15):
     """P_i = (a + i*b) * G, i < n"""
     out = np.zeros((n, 8), dtype=np.uint64)

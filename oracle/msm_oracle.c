@@ -493,6 +493,118 @@ void orc_initial_randomness(const uint64_t *pub_points, const uint64_t *pub_scal
     orc_derive_randomness_from_point(krs, randomness);
 }
 
+/* ---- G1Affine.MultiExp as gnark-crypto computes it (ecc/bn254/multiexp.go, published algorithm restated): the bucket method.
+ * Used as the CPU BASELINE of the multi-exponentiation (tools/gpu_groth16_side.py) and as a fast second oracle at sizes where one
+ * double-and-add per point takes minutes; tests/test_msm_cpu.py pins it to orc_g1_multiexp above.
+ *   bestC:            c = argmin over the implemented widths {4, 5, 8, 16} of 256 * (n + 2^c) / c
+ *   partitionScalars: signed c-bit digits: a digit >= 2^(c-1) becomes digit - 2^c with a carry into the next window
+ *   one task per window (a goroutine per chunk there, a pthread here): bucket[|d| - 1] += / -= point (mixed addition), then
+ *                     the running-sum reduction  sum_b (b + 1) bucket[b]  from the top bucket down
+ *   msmReduceChunk:   Horner over the windows from the top: c doublings, then add the window's sum
+ * Coordinates here are plain Jacobian with the generic addition (the reference uses extended Jacobian buckets; the product XYZZ):
+ * the group elements are the same.                                                                                                  */
+typedef struct {
+    const uint64_t *points;
+    const int32_t *digits; /* [n][W] */
+    size_t n;
+    unsigned W, c;
+    volatile int *next_window;
+    jac_t *window_sum; /* [W] */
+} bkt_job;
+static void *bkt_worker(void *arg) {
+    bkt_job *j = (bkt_job *)arg;
+    const size_t nb = (size_t)1 << (j->c - 1);
+    jac_t *bucket = (jac_t *)malloc(sizeof(jac_t) * nb);
+    for (;;) {
+        const int w = __sync_fetch_and_add(j->next_window, 1);
+        if (w >= (int)j->W) break;
+        for (size_t b = 0; b < nb; b++) jac_set_inf(&bucket[b]);
+        for (size_t i = 0; i < j->n; i++) {
+            const int32_t d = j->digits[i * j->W + (size_t)w];
+            if (d == 0) continue;
+            aff_t p;
+            memcpy(&p, j->points + 8 * i, 64);
+            if (aff_is_inf(&p)) continue;
+            if (d < 0) {
+                fp_t zero = {{0, 0, 0, 0}};
+                fp_sub(&p.y, &zero, &p.y);
+            }
+            jac_t pj;
+            jac_from_aff(&pj, &p);
+            const size_t b = (size_t)(d < 0 ? -d : d) - 1;
+            jac_add(&bucket[b], &bucket[b], &pj);
+        }
+        jac_t run, total;
+        jac_set_inf(&run);
+        jac_set_inf(&total);
+        for (size_t b = nb; b-- > 0;) {
+            jac_add(&run, &run, &bucket[b]);
+            jac_add(&total, &total, &run);
+        }
+        j->window_sum[w] = total;
+    }
+    free(bucket);
+    return NULL;
+}
+void orc_g1_multiexp_buckets(const uint64_t *points, const uint64_t *scalars, size_t n, int scalars_mont, int threads, uint64_t *out) {
+    if (n == 0) {
+        memset(out, 0, 64);
+        return;
+    }
+    static const unsigned implemented[4] = {4, 5, 8, 16};
+    unsigned c = 4;
+    double best = 1e300;
+    for (int k = 0; k < 4; k++) {
+        const double cost = 256.0 * ((double)n + (double)((size_t)1 << implemented[k])) / (double)implemented[k];
+        if (cost < best) best = cost, c = implemented[k];
+    }
+    const unsigned W = 254 / c + 1; /* W * c >= 255: the top digit never carries out for a scalar below q < 2^254 */
+    int32_t *digits = (int32_t *)malloc(sizeof(int32_t) * n * W);
+    for (size_t i = 0; i < n; i++) {
+        uint64_t k[5] = {0, 0, 0, 0, 0};
+        if (scalars_mont) orc_fr_from_mont(scalars + 4 * i, k);
+        else memcpy(k, scalars + 4 * i, 32);
+        uint32_t carry = 0;
+        for (unsigned w = 0; w < W; w++) {
+            const unsigned pos = w * c, word = pos >> 6, off = pos & 63;
+            uint64_t raw = 0;
+            if (word < 4) {
+                raw = k[word] >> off;
+                if (off + c > 64) raw |= k[word + 1] << (64 - off);
+                raw &= ((uint64_t)1 << c) - 1;
+            }
+            raw += carry;
+            if (raw >= ((uint64_t)1 << (c - 1))) {
+                digits[i * W + w] = (int32_t)((int64_t)raw - ((int64_t)1 << c));
+                carry = 1;
+            } else {
+                digits[i * W + w] = (int32_t)raw;
+                carry = 0;
+            }
+        }
+    }
+    if (threads < 1) threads = 1;
+    if ((unsigned)threads > W) threads = (int)W;
+    jac_t *wsum = (jac_t *)malloc(sizeof(jac_t) * W);
+    volatile int next = 0;
+    bkt_job job = {points, digits, n, W, c, &next, wsum};
+    pthread_t *th = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, bkt_worker, &job);
+    for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    jac_t acc;
+    jac_set_inf(&acc);
+    for (unsigned w = W; w-- > 0;) {
+        for (unsigned d = 0; d < c; d++) jac_dbl(&acc, &acc);
+        jac_add(&acc, &acc, &wsum[w]);
+    }
+    aff_t r;
+    jac_to_aff(&r, &acc);
+    memcpy(out, &r, 64);
+    free(digits);
+    free(wsum);
+    free(th);
+}
+
 /* =================================================================================================================================
  * G2: y^2 = x^3 + 3/(9+u) over Fp2 = Fp[u]/(u^2+1) -- G2Affine.MultiExp (prover/gadget/prove.go:277, Bs).
  * gnark-crypto bn254.G2Affine = {X, Y fptower.E2}, E2 = {A0, A1 fp.Element}: 16 words, Montgomery, infinity all zero.

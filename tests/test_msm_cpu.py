@@ -131,6 +131,25 @@ def test_c_oracle_agrees_with_python_oracle(cmsm):
     assert cmsm.point_to_ints(kp) == kp_py and cmsm.unlimbs(rnd) == rnd_py
 
 
+def test_bucket_method_oracle_agrees_with_the_naive_oracle(cmsm):
+    """oracle/msm_oracle.c orc_g1_multiexp_buckets (gnark-crypto's published MultiExp algorithm restated: the CPU baseline and the
+    second oracle the GPU tests use at 2^20 / 2^22) against one double-and-add per point"""
+    rng = random.Random(21)
+    for n in (1, 2, 3, 17, 100, 1000, 20000):
+        pts = cmsm.gen_points(n, a=rng.randrange(cmsm.Q), b=rng.randrange(cmsm.Q))
+        if n >= 17:
+            pts[1] = 0
+            pts[3] = pts[2]
+            pts[5] = cmsm.neg(pts[4])
+        sets = [[rng.randrange(cmsm.Q) for _ in range(n)], [rng.choice([0, 1, cmsm.Q - 1, 1 << 253, (1 << 253) - 1]) for _ in range(n)],
+                [rng.randrange(cmsm.Q)] * n, [rng.randrange(1 << 40) for _ in range(n)]]
+        for vals in (sets if n <= 1000 else sets[:1]):
+            want = cmsm.multiexp(pts, cmsm.scalars_regular(vals))
+            assert np.array_equal(cmsm.multiexp_buckets(pts, cmsm.scalars_regular(vals)), want), n
+            assert np.array_equal(cmsm.multiexp_buckets(pts, cmsm.scalars_mont(vals), mont=True, nthreads=3), want), n
+    assert not cmsm.multiexp_buckets(np.zeros((0, 8), dtype=np.uint64), np.zeros((0, 4), dtype=np.uint64)).any()
+
+
 # ------------------------------------------------------------------------------------------------ 2. the kernel bodies on the host
 def _edge(mod):
     r = (1 << 256) % mod

@@ -207,7 +207,8 @@ def _add_limbs(x, y):
 
 @pytest.mark.parametrize("lg", [20, 22])
 def test_multiexp_full_size_closed_form(cmsm, ecx, lg):
-    """At the sizes of BASELINE.json's batches the oracle's point-by-point sum takes minutes, but on the structured bases
+    """At the sizes of BASELINE.json's batches the oracle's point-by-point sum takes minutes; its bucket-method restatement takes
+    seconds and is compared directly.  Independently of both, on the structured bases
     P_i = (a + i b) G the multi-exponentiation has a closed form: sum_i s_i P_i = (a sum s_i + b sum i s_i) G -- ONE scalar
     multiplication of the oracle.  Also linearity in the scalars on the same bases: MSM(t) + MSM(u) = MSM(t + u)."""
     n = 1 << lg
@@ -234,6 +235,9 @@ def test_multiexp_full_size_closed_form(cmsm, ecx, lg):
     ms = ecx.MultiExp(7, s)
     assert np.array_equal(ms, closed(s))
     assert cmsm.is_on_curve(ms)
+    # and directly against the oracle's bucket-method restatement of gnark-crypto's MultiExp (seconds at this size; pinned to the
+    # point-by-point oracle in tests/test_msm_cpu.py)
+    assert np.array_equal(ms, cmsm.multiexp_buckets(pts, s))
     t, u = rand252(), rand252()
     mt, mu = ecx.MultiExp(7, t), ecx.MultiExp(7, u)
     assert np.array_equal(mt, closed(t)) and np.array_equal(mu, closed(u))
