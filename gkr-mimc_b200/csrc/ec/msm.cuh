@@ -214,20 +214,30 @@ struct KAccum {  // t < max_tasks
         const size_t end_key = (size_t)off[key] + count[key];
         const size_t last = first + pl.T < end_key ? first + pl.T : end_key;
         typename C::X acc = C::x_inf();
-        // the next point is requested before the current addition starts (one gather latency hidden per iteration)
-        uint32_t e_cur = entries[first];
-        typename C::Affine p_cur = C::aff_load(points + (size_t)C::AFF_WORDS * (e_cur & 0x7fffffffu));
-        for (size_t e = first; e < last; e++) {
-            uint32_t e_nxt = 0;
-            typename C::Affine p_nxt = p_cur;
-            if (e + 1 < last) {
-                e_nxt = entries[e + 1];
-                p_nxt = C::aff_load(points + (size_t)C::AFF_WORDS * (e_nxt & 0x7fffffffu));
+        if (C::AFF_WORDS <= 8) {
+            // the next point is requested before the current addition starts (one gather latency hidden per iteration)
+            uint32_t e_cur = entries[first];
+            typename C::Affine p_cur = C::aff_load(points + (size_t)C::AFF_WORDS * (e_cur & 0x7fffffffu));
+            for (size_t e = first; e < last; e++) {
+                uint32_t e_nxt = 0;
+                typename C::Affine p_nxt = p_cur;
+                if (e + 1 < last) {
+                    e_nxt = entries[e + 1];
+                    p_nxt = C::aff_load(points + (size_t)C::AFF_WORDS * (e_nxt & 0x7fffffffu));
+                }
+                if (e_cur & 0x80000000u) p_cur = C::aff_neg(p_cur);
+                acc = C::template add_affine<M>(acc, p_cur);
+                e_cur = e_nxt;
+                p_cur = p_nxt;
             }
-            if (e_cur & 0x80000000u) p_cur = C::aff_neg(p_cur);
-            acc = C::template add_affine<M>(acc, p_cur);
-            e_cur = e_nxt;
-            p_cur = p_nxt;
+        } else {
+            // G2: the point is 32 registers and the addition needs all the others; no prefetch
+            for (size_t e = first; e < last; e++) {
+                const uint32_t ee = entries[e];
+                typename C::Affine p = C::aff_load(points + (size_t)C::AFF_WORDS * (ee & 0x7fffffffu));
+                if (ee & 0x80000000u) p = C::aff_neg(p);
+                acc = C::template add_affine<M>(acc, p);
+            }
         }
         C::x_store(partial + (size_t)C::X_WORDS * t, acc);
     }
