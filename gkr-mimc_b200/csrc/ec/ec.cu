@@ -104,6 +104,36 @@ int ensure(gkrb200ec_ctx* c, void** p, size_t* cap, size_t bytes) {
     return 0;
 }
 
+// Self-check of every point the device hands back (host side, three field products): a result that does not satisfy the curve
+// equation means a base point off the curve or a device fault, and is reported instead of returned.  (A wrong point ON the curve
+// cannot be detected this way; the parity tests are what rules that out.)
+template <class C>
+typename C::El curve_b();
+template <>
+ec::Big8 curve_b<ec::G1>() {  // y^2 = x^3 + 3
+    ec::Big8 t = ec::big_zero();
+    t.v[0] = 3;
+    return ec::f_to_mont<ec::Fp>(t);
+}
+template <>
+ec::Fp2El curve_b<ec::G2>() {  // y^2 = x^3 + 3 / (9 + u)
+    ec::Big8 nine = ec::big_zero(), one = ec::big_zero(), three = ec::big_zero();
+    nine.v[0] = 9, one.v[0] = 1, three.v[0] = 3;
+    ec::Fp2El d, n;
+    d.c0 = ec::f_to_mont<ec::Fp>(nine), d.c1 = ec::f_to_mont<ec::Fp>(one);
+    n.c0 = ec::f_to_mont<ec::Fp>(three), n.c1 = ec::big_zero();
+    return ec::Fp2Mul<ec::FpMulCall>::mul(n, ec::Fp2Base::inv(d));
+}
+template <class C>
+bool on_curve(const uint64_t* aff_mont) {
+    typedef typename C::Field F;
+    typedef typename C::MCall M;
+    const typename C::Affine a = C::aff_load(aff_mont);
+    if (C::aff_is_inf(a)) return true;
+    static const typename C::El b = curve_b<C>();
+    return F::is_zero(F::sub(M::sqr(a.y), F::add(M::mul(M::sqr(a.x), a.x), b)));
+}
+
 // out: affine result, Montgomery (C::AFF_WORDS words) then regular form (C::AFF_WORDS words)
 template <class C>
 int run_msm(gkrb200ec_ctx* c, const uint64_t* d_points, const uint64_t* d_scalars, size_t n, int form, uint64_t* out) {
@@ -142,6 +172,7 @@ int run_msm(gkrb200ec_ctx* c, const uint64_t* d_points, const uint64_t* d_scalar
     if (flag & ec::MSM_ERR_SCALAR_RANGE) return fail(GKRB200EC_ERR_ARG, "multiexp: a regular-form scalar is not reduced (>= q)");
     if (flag) return fail(GKRB200EC_ERR_CUDA, "multiexp: internal digit overflow (flag %u)", flag);
     memcpy(out, c->h_pin, RES * sizeof(uint64_t));
+    if (!on_curve<C>(out)) return fail(GKRB200EC_ERR_CUDA, "multiexp: the result is not on the curve (a base point off the curve, or a device fault)");
     return 0;
 }
 
@@ -176,6 +207,7 @@ int add_points(gkrb200ec_ctx* c, const uint64_t* a, const uint64_t* b, uint64_t*
     CU_TRY(cudaStreamSynchronize(c->stream));
     memcpy(out, c->h_pin, 2 * AW * 8);
     c->st.h2d_bytes += 2 * AW * 8, c->st.d2h_bytes += 2 * AW * 8;
+    if (!on_curve<C>(out)) return fail(GKRB200EC_ERR_CUDA, "point addition: the result is not on the curve (an operand off the curve, or a device fault)");
     return 0;
 }
 

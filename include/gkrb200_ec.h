@@ -33,7 +33,7 @@ typedef struct gkrb200ec_ctx gkrb200ec_ctx;
 typedef enum {
     GKRB200EC_OK = 0,
     GKRB200EC_ERR_ARG = -1,   /* null pointer, unknown base slot, more scalars than bases, scalar >= q in regular form */
-    GKRB200EC_ERR_CUDA = -2,  /* CUDA runtime error or no device */
+    GKRB200EC_ERR_CUDA = -2,  /* CUDA runtime error, no device, or a result that fails the library's self-check (not on the curve) */
     GKRB200EC_ERR_OOM = -3    /* device memory */
 } gkrb200ec_status;
 

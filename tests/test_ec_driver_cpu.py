@@ -99,6 +99,31 @@ def test_multiexp_scalars_in_device_memory(cmsm, ecx, host_driver):
     assert np.array_equal(got, cmsm.multiexp(pts, cmsm.scalars_regular(vals))) and np.array_equal(mont, keep)
 
 
+def test_result_self_check_rejects_points_off_the_curve(cmsm, ecx, host_driver):
+    """every point the device hands back is checked against the curve equation on the host: garbage in (or a device fault) is an error,
+    not an output"""
+    pts = cmsm.gen_points(4)
+    bad = pts.copy()
+    bad[2, 0] ^= np.uint64(2)  # x of one base point disturbed: (x', y) is not on y^2 = x^3 + 3
+    sc = cmsm.scalars_regular([3, 5, 7, 11])
+    assert np.array_equal(ecx.MultiExpPoints(pts, sc), cmsm.multiexp(pts, sc))
+    with pytest.raises(host_driver.GkrB200EcError) as e:
+        ecx.MultiExpPoints(bad, sc)
+    assert e.value.code == -2 and "not on the curve" in str(e.value)
+    with pytest.raises(host_driver.GkrB200EcError):
+        ecx.Add(bad[2], pts[0])
+    g2 = cmsm.g2_gen_points(3)
+    bad2 = g2.copy()
+    bad2[1, 5] ^= np.uint64(1)
+    with pytest.raises(host_driver.GkrB200EcError) as e:
+        ecx.MultiExpPointsG2(bad2, sc[:3])
+    assert "not on the curve" in str(e.value)
+    assert np.array_equal(ecx.MultiExpPointsG2(g2, sc[:3]), cmsm.g2_multiexp(g2, sc[:3]))  # the context survives
+    # with a zero scalar on the bad point the sum never touches it: the result is a valid point and is returned
+    sc0 = cmsm.scalars_regular([3, 5, 0, 11])
+    assert np.array_equal(ecx.MultiExpPoints(bad, sc0), cmsm.multiexp(pts, sc0))
+
+
 def test_g2_add(cmsm, ecx):
     gpu_msm.test_g2_add_on_the_device(cmsm, ecx)
 
