@@ -325,6 +325,26 @@ class EcContext:
                                             _p(r), _p(s), _p(ar), _p(bs), _p(krs)))
         return ar, bs, krs
 
+    def MultiExpSharded(self, slot, scalars_local, form=SCALARS_REGULAR, group=None):
+        """One multi-exponentiation over several GPUs, one process per GPU (torch.distributed): rank r holds ITS slice of the bases in
+        `slot` and passes the matching slice of the scalars; no data-path collective -- the only exchange is an all-gather of the
+        partial sums (64 bytes per rank), which every rank then adds in rank order (a sum of points has one affine form: identical
+        bytes on every rank, equal to the single-GPU result)."""
+        import torch
+        import torch.distributed as dist
+        part = self.MultiExp(slot, scalars_local, form)
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return part
+        t = torch.from_numpy(part.view(np.int64).copy())
+        if dist.get_backend(group) == "nccl":
+            t = t.to("cuda:%d" % self.device)
+        parts = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(parts, t, group=group)
+        acc = np.zeros(8, dtype=np.uint64)
+        for g in parts:
+            acc = self.Add(acc, g.cpu().numpy().view(np.uint64))
+        return acc
+
     def set_plan(self, window_bits=0, task_size=0):
         check(lib().gkrb200ec_set_plan(self._h, window_bits, task_size))
 

@@ -175,3 +175,47 @@ def test_descending_thread_order_gives_the_same_bytes(cmsm, cfft):
     env = dict(os.environ, EC_HOSTBUILD_REVERSE="1")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0 and "reverse ok" in out.stdout, out.stderr[-2000:]
+
+
+def _sharded_worker(rank, world, port, n, out):
+    """one rank of the sharded multi-exponentiation: the host build of the driver stands in for the rank's GPU"""
+    import torch.distributed as dist
+    for p_ in (os.path.join(ROOT, "gkr-mimc_b200"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p_)
+    import cmsm
+    from gkrb200 import ec
+    ec._lib = ec._bind(ctypes.CDLL(SO))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pts = cmsm.gen_points(n)
+        vals = [(i * i * 0x9E3779B97F4A7C15 + 99) % cmsm.Q for i in range(n)]
+        lo, hi = n * rank // world, n * (rank + 1) // world  # contiguous slices; any partition of the index set works
+        with ec.EcContext(device=0) as c:
+            c.SetBases(0, pts[lo:hi])
+            got = c.MultiExpSharded(0, cmsm.scalars_regular(vals[lo:hi]))
+        want = cmsm.multiexp(pts, cmsm.scalars_regular(vals))
+        out.put((rank, bool(np.array_equal(got, want))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_multiexp_over_gloo(world):
+    """EcContext.MultiExpSharded: every rank multiplies its slice, the partial sums are all-gathered and added -- identical bytes on
+    every rank, equal to the oracle's full sum (world_size 2 and 4, gloo, the host build of the driver on each rank)"""
+    import socket
+    import torch.multiprocessing as mp
+    build_hostbuild()
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, world, port, 203, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert res == [(r, True) for r in range(world)]
