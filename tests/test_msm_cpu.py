@@ -428,7 +428,7 @@ def test_emulated_g2_multiexp_matches_oracle(cmsm, emu, n):
             continue
         reg = cmsm.scalars_regular(vals)
         want = cmsm.g2_multiexp(pts, reg)
-        for c, T in ([(0, 0), (2, 0), (3, 1), (16, 0)] if n <= 64 else [(0, 0), (5, 3)]):
+        for c, T in ([(0, 0), (2, 0), (3, 1), (16, 0)] if n <= 2 else [(0, 0), (2, 0), (3, 1)] if n <= 64 else [(0, 0), (5, 3)]):  # 2^15 Fp2 buckets per window are slow on the CPU
             for rev in (0, 1):
                 out = np.zeros(32, dtype=np.uint64)
                 rc = emu.emu_g2_msm(_p(pts), _p(reg), ctypes.c_size_t(n), 0, c, T, rev, _p(out), None)
